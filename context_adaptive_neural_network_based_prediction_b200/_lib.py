@@ -1,0 +1,67 @@
+"""ctypes binding of libpnn_cuda.so (the C ABI declared in include/pnn_cuda.h).
+
+There is no fallback: if the shared library is missing the import fails loudly, and
+`pnn_create` itself fails when no sm_100 GPU is present.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libpnn_cuda.so')
+
+# every symbol include/pnn_cuda.h declares
+EXPORTS = (
+    'pnn_create', 'pnn_destroy', 'pnn_last_error', 'pnn_load_net', 'pnn_set_precision',
+    'pnn_set_context', 'pnn_predict_hm', 'pnn_predict_batch', 'pnn_predict_image_blocks',
+    'pnn_predict_batch_device', 'pnn_predict_image_blocks_device', 'pnn_launch_count',
+    'pnn_last_hm_device_ms', 'pnn_version',
+)
+
+PRECISION_FP32 = 0
+PRECISION_BF16X3 = 1
+
+_lib = None
+
+
+def load():
+    """Loads libpnn_cuda.so once; raises if it has not been built (run `python -c "import __graft_entry__ as g; g.build()"`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError('%s is missing: build it with __graft_entry__.build() (make -C %s). '
+                          'There is no CPU fallback.' % (LIB_PATH, os.path.dirname(LIB_PATH)))
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i32, i64 = c.c_void_p, c.c_int, c.c_int64
+    lib.pnn_create.argtypes = [c.c_char_p, c.c_float, i32, i32, c.POINTER(vp)]
+    lib.pnn_create.restype = i32
+    lib.pnn_destroy.argtypes = [vp]
+    lib.pnn_destroy.restype = None
+    lib.pnn_last_error.argtypes = [vp]
+    lib.pnn_last_error.restype = c.c_char_p
+    lib.pnn_load_net.argtypes = [vp, c.c_char_p]
+    lib.pnn_load_net.restype = i32
+    lib.pnn_set_precision.argtypes = [vp, i32]
+    lib.pnn_set_precision.restype = i32
+    lib.pnn_set_context.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32]
+    lib.pnn_set_context.restype = i32
+    lib.pnn_predict_hm.argtypes = [vp, i32, vp, i32]
+    lib.pnn_predict_hm.restype = i32
+    lib.pnn_predict_batch.argtypes = [vp, i32, i32, vp, vp, i64, vp]
+    lib.pnn_predict_batch.restype = i32
+    lib.pnn_predict_image_blocks.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.pnn_predict_image_blocks.restype = i32
+    lib.pnn_predict_batch_device.argtypes = [vp, i32, i32, vp, vp, i64, vp, vp]
+    lib.pnn_predict_batch_device.restype = i32
+    lib.pnn_predict_image_blocks_device.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32,
+                                                    vp, vp, vp, vp]
+    lib.pnn_predict_image_blocks_device.restype = i32
+    lib.pnn_launch_count.argtypes = [vp]
+    lib.pnn_launch_count.restype = i64
+    lib.pnn_last_hm_device_ms.argtypes = [vp]
+    lib.pnn_last_hm_device_ms.restype = c.c_float
+    lib.pnn_version.argtypes = []
+    lib.pnn_version.restype = c.c_char_p
+    _lib = lib
+    return lib

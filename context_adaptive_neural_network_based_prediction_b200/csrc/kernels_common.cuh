@@ -1,0 +1,52 @@
+// Device helpers shared by the kernels of libpnn_cuda.
+#pragma once
+
+#include "pnn_internal.h"
+
+namespace pnn {
+
+__device__ __forceinline__ float leaky_relu(float x) {
+    // reference pnn/tfutils.py:192: tf.maximum(0.1*input, input)
+    return fmaxf(0.1f * x, x);
+}
+
+// value -> (hi, lo) bf16 with hi + lo ~= value to 16 mantissa bits
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ float act_load(const Act& a, int64_t idx) {
+    if (SPLIT) {
+        return __bfloat162float(((const __nv_bfloat16*)a.p0)[idx]) + __bfloat162float(((const __nv_bfloat16*)a.p1)[idx]);
+    }
+    return ((const float*)a.p0)[idx];
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void act_store(const Act& a, int64_t idx, float v) {
+    if (SPLIT) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        ((__nv_bfloat16*)a.p0)[idx] = hi;
+        ((__nv_bfloat16*)a.p1)[idx] = lo;
+    } else {
+        ((float*)a.p0)[idx] = v;
+    }
+}
+
+// Fused epilogue of the last layer: raw output, and round(clip(p + mean, 0, 255)).
+//   half-even: numpy.round, reference tools/tools.py:49
+//   half-away: std::round, reference TComPrediction.cpp(substitution):632
+__device__ __forceinline__ void final_store(const FinalOut& f, int64_t idx, float p) {
+    if (f.raw) f.raw[idx] = p;
+    if (f.u8 || f.i32) {
+        float v = fminf(fmaxf(p + f.mean, 0.f), 255.f);
+        float r = f.round_mode == 0 ? rintf(v) : roundf(v);
+        if (f.u8) f.u8[idx] = (uint8_t)r;
+        if (f.i32) f.i32[idx] = (int32_t)r;
+    }
+}
+
+}  // namespace pnn

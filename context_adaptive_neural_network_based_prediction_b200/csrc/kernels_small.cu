@@ -1,0 +1,296 @@
+// HBM-bound kernels of the PNN path: fused context gather, first convolution (1 input channel),
+// channel-wise merger, last transposed convolution (1 output channel) with the fused epilogue, PSNR.
+#include "kernels_common.cuh"
+
+namespace pnn {
+
+static inline int grid_for(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    const int64_t cap = 148 * 32;   // grid-stride beyond 32 waves of the 148 SMs
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused gather from uint8 images (reference sets/common.py:99-109 slicing, :454-461 mean + masks,
+// :467-472 FC flattening = above row-major then left row-major).
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void gather_image_kernel(GatherLaunch L) {
+    const int W = L.W;
+    const int na = 3 * W * W, nl = 2 * W * W, per = na + nl;
+    const int64_t total = L.n * per;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx / per;
+        const int e = (int)(idx - i * per);
+        const int img = L.image_index ? L.image_index[i] : 0;
+        const int r0 = L.rows[i], c0 = L.cols[i];
+        int r, c;
+        bool masked;
+        if (e < na) {
+            const int rr = e / (3 * W), cc = e - rr * 3 * W;
+            r = r0 - W + rr;
+            c = c0 - W + cc;
+            masked = cc >= 3 * W - L.mask_w;
+        } else {
+            const int e2 = e - na;
+            const int rr = e2 / W, cc = e2 - rr * W;
+            r = r0 + rr;
+            c = c0 - W + cc;
+            masked = rr >= 2 * W - L.mask_h;
+        }
+        float v = 0.f;
+        if (!masked && r >= 0 && r < L.H && c >= 0 && c < L.Wimg) {
+            v = (float)L.images[((int64_t)img * L.H + r) * L.Wimg + c] - L.mean;
+        }
+        if (e < na) {
+            act_store<SPLIT>(L.above, i * L.pitch_above + e, v);
+        } else {
+            act_store<SPLIT>(L.left, i * L.pitch_left + (e - na), v);
+        }
+    }
+}
+
+int launch_gather_image(const GatherLaunch& L, cudaStream_t stream) {
+    const int64_t total = L.n * 5 * L.W * L.W;
+    if (total == 0) return 0;
+    if (L.split) gather_image_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(L);
+    else gather_image_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// HM gather (reference extraction_context.cpp:56-205).  The host staged the raw int pixels of the
+// L-shaped context; here: int -> float, minus mean, and the availability masking:
+//   above columns [0, W)             always copied (Portion (1), extraction_context.cpp:119-127)
+//   above columns W + i*unit_w ...   copied iff above unit i is available (:149-166)
+//   left rows [0, left_rows_valid)   copied; the reference writer only advances on available units
+//                                    (:189-205), so the copied rows are the first n_avail*unit_h ones.
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void gather_hm_kernel(GatherHmLaunch L) {
+    const int W = L.W;
+    const int na = 3 * W * W, total = 5 * W * W;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        float v = (float)L.staged[e] - L.mean;
+        if (e < na) {
+            const int cc = e % (3 * W);
+            if (cc >= W) {
+                const int u = (cc - W) / L.unit_w;
+                const uint32_t bit = u < 32 ? (L.above_mask_lo >> u) & 1u : (L.above_mask_hi >> (u - 32)) & 1u;
+                if (!bit) v = 0.f;
+            }
+            act_store<SPLIT>(L.above, e, v);
+        } else {
+            const int e2 = e - na;
+            if (e2 / W >= L.left_rows_valid) v = 0.f;
+            act_store<SPLIT>(L.left, e2, v);
+        }
+    }
+}
+
+int launch_gather_hm(const GatherHmLaunch& L, cudaStream_t stream) {
+    const int total = 5 * L.W * L.W;
+    const int grid = (total + 255) / 256;
+    if (L.split) gather_hm_kernel<true><<<grid, 256, 0, stream>>>(L);
+    else gather_hm_kernel<false><<<grid, 256, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void convert_input_kernel(const float* __restrict__ src, Act dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        act_store<SPLIT>(dst, i, src[i]);
+    }
+}
+
+int launch_convert_input(const float* src, Act dst, int64_t n, int split, cudaStream_t stream) {
+    if (n == 0) return 0;
+    if (split) convert_input_kernel<true><<<grid_for(n, 256), 256, 0, stream>>>(src, dst, n);
+    else convert_input_kernel<false><<<grid_for(n, 256), 256, 0, stream>>>(src, dst, n);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// First convolution of a branch: 1 input channel, k x k, stride s, SAME padding, + bias, LeakyReLU
+// (reference pnn/components.py:33-46, pnn/tfutils.py:134-139).  One thread per output value, the
+// output channel fastest so that the k*k input pixels are warp broadcasts and the stores coalesce.
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void conv0_kernel(Conv0Launch L) {
+    const int64_t per = (int64_t)L.OH * L.OW * L.Cout;
+    const int64_t total = L.n * per;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % L.Cout);
+        int64_t pix = idx / L.Cout;
+        const int ox = (int)(pix % L.OW);
+        pix /= L.OW;
+        const int oy = (int)(pix % L.OH);
+        const int64_t b = pix / L.OH;
+        const float* in = L.in + b * L.IH * L.IW;
+        float acc = 0.f;
+        for (int ky = 0; ky < L.k; ++ky) {
+            const int iy = oy * L.stride + ky - L.pad;
+            if (iy < 0 || iy >= L.IH) continue;
+            for (int kx = 0; kx < L.k; ++kx) {
+                const int ix = ox * L.stride + kx - L.pad;
+                if (ix < 0 || ix >= L.IW) continue;
+                acc = fmaf(in[iy * L.IW + ix], L.w[(ky * L.k + kx) * L.Cout + co], acc);
+            }
+        }
+        act_store<SPLIT>(L.out, idx, leaky_relu(acc + L.bias[co]));
+    }
+}
+
+int launch_conv0(const Conv0Launch& L, cudaStream_t stream) {
+    const int64_t total = (int64_t)L.n * L.OH * L.OW * L.Cout;
+    if (total == 0) return 0;
+    if (L.split) conv0_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(L);
+    else conv0_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Channel-wise fully-connected merger + LeakyReLU (reference pnn/tfutils.py:60-73,
+// pnn/components.py:225-231): per channel c, the 48 values of the above map (row-major) followed by
+// the 32 values of the left map are fully connected to 16 outputs.  One thread per (sample, channel),
+// channel fastest; the weights were transposed on the host to [80][16][C] so that loads coalesce.
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void merger_kernel(MergerLaunch L) {
+    const int64_t total = (int64_t)L.n * L.C;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % L.C);
+        const int64_t b = idx / L.C;
+        float acc[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) acc[p] = 0.f;
+        for (int q = 0; q < 80; ++q) {
+            const float x = q < 48 ? act_load<SPLIT>(L.in0, (b * 48 + q) * L.C + c)
+                                   : act_load<SPLIT>(L.in1, (b * 32 + (q - 48)) * L.C + c);
+            const float* w = L.w + (int64_t)q * 16 * L.C + c;
+#pragma unroll
+            for (int p = 0; p < 16; ++p) acc[p] = fmaf(x, w[p * L.C], acc[p]);
+        }
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            act_store<SPLIT>(L.out, (b * 16 + p) * L.C + c, leaky_relu(acc[p] + L.bias[p * L.C + c]));
+        }
+    }
+}
+
+int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
+    const int64_t total = (int64_t)L.n * L.C;
+    if (total == 0) return 0;
+    if (L.split) merger_kernel<true><<<grid_for(total, 128), 128, 0, stream>>>(L);
+    else merger_kernel<false><<<grid_for(total, 128), 128, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Last transposed convolution: Cin -> 1 channel, linear, fused with the output epilogue
+// (reference pnn/components.py:237-259, pnn/tfutils.py:455-462; epilogue TComPrediction.cpp:621-635 /
+// tools/tools.py:49).  Gather form with a fixed tap order (ky, kx, ci ascending):
+//   out[y, x] = bias + sum_{ky,kx : (y+pad-ky) % s == 0 ...} in[(y+pad-ky)/s, (x+pad-kx)/s, :] . w[ky, kx, :]
+// One thread per output pixel.
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void tconv_last_kernel(TconvLastLaunch L) {
+    const int OH = L.IH * L.stride, OW = L.IW * L.stride;
+    const int64_t total = (int64_t)L.n * OH * OW;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % OW);
+        const int y = (int)((idx / OW) % OH);
+        const int64_t b = idx / ((int64_t)OW * OH);
+        float acc = 0.f;
+        for (int ky = 0; ky < L.k; ++ky) {
+            const int ty = y + L.pad - ky;
+            if (ty < 0 || ty % L.stride) continue;
+            const int iy = ty / L.stride;
+            if (iy >= L.IH) continue;
+            for (int kx = 0; kx < L.k; ++kx) {
+                const int tx = x + L.pad - kx;
+                if (tx < 0 || tx % L.stride) continue;
+                const int ix = tx / L.stride;
+                if (ix >= L.IW) continue;
+                const int64_t base = ((b * L.IH + iy) * L.IW + ix) * L.Cin;
+                const float* w = L.w + (ky * L.k + kx) * L.Cin;
+                if (SPLIT) {
+                    const uint4* ph = (const uint4*)((const __nv_bfloat16*)L.in.p0 + base);
+                    const uint4* pl = (const uint4*)((const __nv_bfloat16*)L.in.p1 + base);
+                    for (int ci = 0; ci < L.Cin; ci += 8) {
+                        const uint4 h = ph[ci >> 3], l = pl[ci >> 3];
+                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float a0 = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                            const float a1 = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+                            acc = fmaf(a0, w[ci + 2 * j], acc);
+                            acc = fmaf(a1, w[ci + 2 * j + 1], acc);
+                        }
+                    }
+                } else {
+                    const float4* p = (const float4*)((const float*)L.in.p0 + base);
+                    for (int ci = 0; ci < L.Cin; ci += 4) {
+                        const float4 a = p[ci >> 2];
+                        acc = fmaf(a.x, w[ci], acc);
+                        acc = fmaf(a.y, w[ci + 1], acc);
+                        acc = fmaf(a.z, w[ci + 2], acc);
+                        acc = fmaf(a.w, w[ci + 3], acc);
+                    }
+                }
+            }
+        }
+        final_store(L.fin, idx, acc + L.bias);
+    }
+}
+
+int launch_tconv_last(const TconvLastLaunch& L, cudaStream_t stream) {
+    const int64_t total = (int64_t)L.n * L.IH * L.stride * L.IW * L.stride;
+    if (total == 0) return 0;
+    if (L.split) tconv_last_kernel<true><<<grid_for(total, 128), 128, 0, stream>>>(L);
+    else tconv_last_kernel<false><<<grid_for(total, 128), 128, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PSNR per block (reference tools/tools.py:364-401): 10*log10(255^2 / (mean((a-b)^2) + 1e-6)), float64.
+// One warp per block; the sum of squared differences is an exact integer.
+// ---------------------------------------------------------------------------------------------
+__global__ void psnr_kernel(const uint8_t* __restrict__ images, const int32_t* __restrict__ image_index,
+                            const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int64_t n,
+                            int H, int Wimg, int W, const uint8_t* __restrict__ pred, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        const int img = image_index ? image_index[i] : 0;
+        const uint8_t* base = images + ((int64_t)img * H + rows[i]) * Wimg + cols[i];
+        const uint8_t* p = pred + i * W * W;
+        int sse = 0;
+        for (int e = lane; e < W * W; e += 32) {
+            const int r = e / W, c = e - r * W;
+            const int d = (int)base[(int64_t)r * Wimg + c] - (int)p[e];
+            sse += d * d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
+        if (lane == 0) {
+            const double mse = (double)sse / (double)(W * W);
+            out[i] = 10. * log10(255. * 255. / (mse + 1.e-6));
+        }
+    }
+}
+
+int launch_psnr(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols,
+                int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream) {
+    if (n == 0) return 0;
+    psnr_kernel<<<grid_for(n * 32, 256), 256, 0, stream>>>(images, image_index, rows, cols, n, H, Wimg, W, pred_u8, out);
+    return 1;
+}
+
+}  // namespace pnn

@@ -1,0 +1,996 @@
+// Host side of libpnn_cuda: weight loading / re-packing, network plans, workspaces, the C ABI.
+#include "../../include/pnn_cuda.h"
+#include "pnn_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <sstream>
+
+using namespace pnn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e_));       \
+        }                                                                                       \
+    } while (0)
+
+// reference pnn/PredictionNeuralNetwork.py:126-132
+std::vector<int> strides_branch(int w) {
+    switch (w) {
+        case 4: return {1, 1};
+        case 8: return {2, 1};
+        case 16: return {2, 1, 2, 1};
+        case 32: return {2, 2, 1, 2, 1};
+        case 64: return {2, 2, 2, 2, 1};
+    }
+    return {};
+}
+
+// TensorFlow 'SAME': pad_before of a k x k window, stride s, input n
+int same_pad_before(int n, int k, int s) {
+    const int out = (n + s - 1) / s;
+    const int total = std::max((out - 1) * s + k - n, 0);
+    return total / 2;
+}
+
+uint16_t bf16_rn(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float bf16_to_float(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void reserve(size_t n) {
+        if (n <= bytes) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        CUDA_TRY(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+template <typename T>
+T* upload(const std::vector<T>& v, std::vector<std::unique_ptr<DevBuf>>& keep) {
+    keep.emplace_back(new DevBuf());
+    keep.back()->reserve(std::max<size_t>(v.size() * sizeof(T), 16));
+    CUDA_TRY(cudaMemcpy(keep.back()->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return (T*)keep.back()->p;
+}
+
+enum StepKind { STEP_GEMM, STEP_CONV0, STEP_MERGER, STEP_TCONV_LAST };
+
+struct Step {
+    StepKind kind;
+    // buffers (indices into Net::buf_elems / workspace); -1 = unused
+    int in0 = -1, in1 = -1, out = -1;
+    bool is_final = false;
+    // GEMM
+    GemmGeom g{};
+    const float* d_w32 = nullptr;
+    const uint8_t* d_wt = nullptr;
+    const float* d_bias = nullptr;
+    // conv0
+    int IH = 0, IW = 0, OH = 0, OW = 0, C = 0, k = 0, stride = 0, pad = 0;
+    float bias_scalar = 0.f;
+};
+
+struct Net {
+    int W = 0;
+    bool is_fc = false;
+    std::vector<Step> steps;
+    std::vector<int64_t> buf_elems;   // per-sample elements of every activation buffer
+    std::vector<bool> buf_fp32_only;  // context inputs of conv nets are always fp32
+    int in_above = -1, in_left = -1;  // conv: context buffers; FC: in_above = flat context
+    std::vector<std::unique_ptr<DevBuf>> dev;   // weights
+    int64_t param_count = 0;
+    // workspace
+    int64_t cap = 0;
+    std::vector<std::unique_ptr<DevBuf>> ws0, ws1;
+    DevBuf out_raw, out_u8, out_i32, out_psnr;
+};
+
+struct FlatFile {
+    int width = 0;
+    bool is_fc = false;
+    std::map<std::string, std::vector<float>> t;
+    std::map<std::string, std::vector<int>> shape;
+};
+
+FlatFile read_flat(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open weights file \"" + path + "\"");
+    std::vector<char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (data.size() < 24 || memcmp(data.data(), "PNNWv001", 8) != 0) {
+        throw std::runtime_error("\"" + path + "\" is not a PNNW flat binary");
+    }
+    auto u32 = [&](size_t pos) {
+        if (pos + 4 > data.size()) throw std::runtime_error("truncated weights file \"" + path + "\"");
+        uint32_t v;
+        memcpy(&v, data.data() + pos, 4);
+        return v;
+    };
+    auto u64 = [&](size_t pos) {
+        if (pos + 8 > data.size()) throw std::runtime_error("truncated weights file \"" + path + "\"");
+        uint64_t v;
+        memcpy(&v, data.data() + pos, 8);
+        return v;
+    };
+    FlatFile out;
+    out.width = (int)u32(8);
+    out.is_fc = u32(12) != 0;
+    const uint32_t n = u32(16);
+    size_t pos = 24;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t ln = u32(pos);
+        pos += 4;
+        if (pos + ln > data.size()) throw std::runtime_error("truncated weights file \"" + path + "\"");
+        std::string name(data.data() + pos, ln);
+        pos += ln;
+        const uint32_t rank = u32(pos);
+        pos += 4;
+        std::vector<int> dims;
+        size_t count = 1;
+        for (uint32_t r = 0; r < rank; ++r) {
+            dims.push_back((int)u32(pos));
+            count *= dims.back();
+            pos += 4;
+        }
+        const uint64_t off = u64(pos), nbytes = u64(pos + 8);
+        pos += 16;
+        if (nbytes != count * 4 || off + nbytes > data.size()) {
+            throw std::runtime_error("bad tensor table entry \"" + name + "\" in \"" + path + "\"");
+        }
+        std::vector<float> v(count);
+        memcpy(v.data(), data.data() + off, nbytes);
+        out.t[name] = std::move(v);
+        out.shape[name] = dims;
+    }
+    return out;
+}
+
+const std::vector<float>& need(const FlatFile& ff, const std::string& name, const std::vector<int>& shape) {
+    auto it = ff.t.find(name);
+    if (it == ff.t.end()) throw std::runtime_error("weights file lacks tensor \"" + name + "\"");
+    if (ff.shape.at(name) != shape) throw std::runtime_error("tensor \"" + name + "\" has an unexpected shape");
+    return it->second;
+}
+
+// [K][N] fp32 -> pre-swizzled bf16 hi/lo tiles (layout in pnn_internal.h / kernel_gemm_tc.cu)
+std::vector<uint8_t> make_tc_tiles(const std::vector<float>& w, int K, int N) {
+    std::vector<uint8_t> out(tc_total_bytes(N, K), 0);
+    const int num_kb = tc_num_kb(K), num_nt = tc_num_nt(N);
+    for (int nt = 0; nt < num_nt; ++nt) {
+        const int bn = tc_tile_bn(N, nt);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            uint8_t* hi = out.data() + tc_tile_offset(N, K, nt, kb);
+            uint8_t* lo = hi + (size_t)bn * 128;
+            for (int r = 0; r < bn; ++r) {
+                const int n = nt * TC_BN + r;
+                if (n >= N) continue;
+                for (int kk = 0; kk < TC_BK; ++kk) {
+                    const int k = kb * TC_BK + kk;
+                    if (k >= K) continue;
+                    const float v = w[(size_t)k * N + n];
+                    const uint16_t h = bf16_rn(v);
+                    const uint16_t l = bf16_rn(v - bf16_to_float(h));
+                    const size_t o = (size_t)r * 128 + (size_t)(((kk >> 3) ^ (r & 7)) << 4) + (size_t)(kk & 7) * 2;
+                    memcpy(hi + o, &h, 2);
+                    memcpy(lo + o, &l, 2);
+                }
+            }
+        }
+    }
+    return out;
+}
+
+int add_buf(Net& net, int64_t elems, bool fp32_only = false) {
+    net.buf_elems.push_back(elems);
+    net.buf_fp32_only.push_back(fp32_only);
+    return (int)net.buf_elems.size() - 1;
+}
+
+void add_gemm_weights(Net& net, Step& st, const std::vector<float>& w_kn, const std::vector<float>& bias) {
+    st.d_w32 = upload(w_kn, net.dev);
+    st.d_wt = upload(make_tc_tiles(w_kn, st.g.K, st.g.N), net.dev);
+    st.d_bias = upload(bias, net.dev);
+}
+
+// reference pnn/components.py:103-180
+void build_fc(Net& net, const FlatFile& ff) {
+    const int W = net.W;
+    const int dims[5] = {5 * W * W, 1200, 1200, 1200, W * W};
+    int cur = add_buf(net, dims[0]);
+    net.in_above = cur;
+    for (int i = 0; i < 4; ++i) {
+        Step st;
+        st.kind = STEP_GEMM;
+        GemmGeom& g = st.g;
+        g.P = 1; g.OW = 1; g.Cin = dims[i]; g.TH = 1; g.TW = 1; g.IH = 1; g.IW = 1;
+        g.sy_o = 0; g.sy_t = 0; g.cy = 0; g.sx_o = 0; g.sx_t = 0; g.cx = 0;
+        g.in_sample_stride = dims[i];
+        g.N = dims[i + 1]; g.K = dims[i];
+        g.OHf = 1; g.OWf = 1; g.osy = 1; g.ooy = 0; g.osx = 1; g.oox = 0;
+        g.out_sample_stride = dims[i + 1];
+        g.leaky = i != 3;
+        const std::string sfx = std::to_string(i);
+        add_gemm_weights(net, st, need(ff, "fully_connected/weights_" + sfx, {dims[i], dims[i + 1]}),
+                         need(ff, "fully_connected/biases_" + sfx, {dims[i + 1]}));
+        net.param_count += (int64_t)dims[i] * dims[i + 1] + dims[i + 1];
+        st.in0 = cur;
+        if (i == 3) {
+            st.is_final = true;
+        } else {
+            st.out = add_buf(net, dims[i + 1]);
+            cur = st.out;
+        }
+        net.steps.push_back(st);
+    }
+}
+
+// reference pnn/components.py:10-101, 182-261
+void build_conv(Net& net, const FlatFile& ff) {
+    const int W = net.W;
+    const std::vector<int> strides = strides_branch(W);
+    if (strides.empty()) throw std::runtime_error("unsupported width for a convolutional PNN");
+    int branch_out[2] = {-1, -1};
+    int C = 32;
+    for (int br = 0; br < 2; ++br) {
+        const std::string bname = br == 0 ? "above" : "left";
+        int h = br == 0 ? W : 2 * W, w = br == 0 ? 3 * W : W;
+        int cur = add_buf(net, (int64_t)h * w, true);
+        (br == 0 ? net.in_above : net.in_left) = cur;
+        int c_in = 1, c = 32;
+        for (size_t i = 0; i < strides.size(); ++i) {
+            const int s = strides[i], k = 2 * s + 1;
+            c *= s;
+            const int oh = h / s, ow = w / s;
+            const int pad_y = same_pad_before(h, k, s), pad_x = same_pad_before(w, k, s);
+            const std::string p = "convolutional/branch_" + bname + "/convolution_" + std::to_string(i) + "/";
+            const std::vector<float>& wt = need(ff, p + "weights", {k, k, c_in, c});
+            const std::vector<float>& bs = need(ff, p + "biases", {c});
+            net.param_count += (int64_t)wt.size() + bs.size();
+            Step st;
+            st.in0 = cur;
+            st.out = add_buf(net, (int64_t)oh * ow * c);
+            if (i == 0) {
+                st.kind = STEP_CONV0;
+                st.IH = h; st.IW = w; st.OH = oh; st.OW = ow; st.C = c; st.k = k; st.stride = s; st.pad = pad_y;
+                if (pad_x != pad_y) throw std::runtime_error("unexpected asymmetric padding");
+                st.d_w32 = upload(wt, net.dev);          // [k*k][Cout] because Cin == 1
+                st.d_bias = upload(bs, net.dev);
+            } else {
+                st.kind = STEP_GEMM;
+                GemmGeom& g = st.g;
+                g.P = oh * ow; g.OW = ow; g.Cin = c_in; g.TH = k; g.TW = k; g.IH = h; g.IW = w;
+                g.sy_o = s; g.sy_t = 1; g.cy = -pad_y; g.sx_o = s; g.sx_t = 1; g.cx = -pad_x;
+                g.in_sample_stride = (int64_t)h * w * c_in;
+                g.N = c; g.K = k * k * c_in;
+                g.OHf = oh; g.OWf = ow; g.osy = 1; g.ooy = 0; g.osx = 1; g.oox = 0;
+                g.out_sample_stride = (int64_t)oh * ow * c;
+                g.leaky = 1;
+                add_gemm_weights(net, st, wt, bs);       // TF [k,k,Cin,Cout] is already [K][N]
+            }
+            net.steps.push_back(st);
+            cur = st.out;
+            h = oh; w = ow; c_in = c;
+        }
+        branch_out[br] = cur;
+        C = c;
+        if ((br == 0 && (h != 4 || w != 12)) || (br == 1 && (h != 8 || w != 4))) {
+            throw std::runtime_error("unexpected branch output map");
+        }
+    }
+    // merger (reference pnn/tfutils.py:8-73): weights [C,80,16] -> [80][16][C], biases [C,16] -> [16][C]
+    {
+        const std::string p = "convolutional/merger/channelwise_fully_connected_merger/";
+        const std::vector<float>& wt = need(ff, p + "weights", {C, 80, 16});
+        const std::vector<float>& bs = need(ff, p + "biases", {C, 16});
+        net.param_count += (int64_t)wt.size() + bs.size();
+        std::vector<float> wtr((size_t)80 * 16 * C), btr((size_t)16 * C);
+        for (int c = 0; c < C; ++c) {
+            for (int q = 0; q < 80; ++q)
+                for (int o = 0; o < 16; ++o) wtr[((size_t)q * 16 + o) * C + c] = wt[((size_t)c * 80 + q) * 16 + o];
+            for (int o = 0; o < 16; ++o) btr[(size_t)o * C + c] = bs[(size_t)c * 16 + o];
+        }
+        Step st;
+        st.kind = STEP_MERGER;
+        st.in0 = branch_out[0];
+        st.in1 = branch_out[1];
+        st.out = add_buf(net, (int64_t)16 * C);
+        st.C = C;
+        st.d_w32 = upload(wtr, net.dev);
+        st.d_bias = upload(btr, net.dev);
+        net.steps.push_back(st);
+    }
+    int cur = net.steps.back().out;
+    int h = 4, w = 4, c = C;
+    const int nb = (int)strides.size();
+    for (int i = 0; i < nb; ++i) {
+        const int s = strides[nb - 1 - i], k = 2 * s + 1;
+        const bool last = i == nb - 1;
+        const int c_out = last ? 1 : c / s;
+        const int oh = h * s, ow = w * s;
+        // conv2d_transpose 'SAME' is the gradient of the forward conv on the (oh, ow) map:
+        // out[y] = sum over (iy, ky) with iy*s + ky - pad == y   (reference pnn/tfutils.py:455-459)
+        const int pad = same_pad_before(oh, k, s);
+        const std::string p = "convolutional/merger/transpose_convolution_" + std::to_string(i) + "/";
+        const std::vector<float>& wt = need(ff, p + "weights", {k, k, c_out, c});
+        const std::vector<float>& bs = need(ff, p + "biases", {c_out});
+        net.param_count += (int64_t)wt.size() + bs.size();
+        if (last) {
+            Step st;
+            st.kind = STEP_TCONV_LAST;
+            st.in0 = cur;
+            st.is_final = true;
+            st.IH = h; st.IW = w; st.C = c; st.k = k; st.stride = s; st.pad = pad;
+            st.d_w32 = upload(wt, net.dev);              // [k*k][1][Cin]
+            st.bias_scalar = bs[0];
+            net.steps.push_back(st);
+        } else {
+            const int out_buf = add_buf(net, (int64_t)oh * ow * c_out);
+            // one GEMM per output phase (py, px): output y = s*oy + py uses taps ky = ky0 + s*j with
+            // ky0 = (py + pad) % s, reading input row iy = oy + (py + pad - ky0)/s - j.
+            for (int py = 0; py < s; ++py) {
+                for (int px = 0; px < s; ++px) {
+                    const int ky0 = (py + pad) % s, kx0 = (px + pad) % s;
+                    const int th = (k - ky0 + s - 1) / s, tw = (k - kx0 + s - 1) / s;
+                    Step st;
+                    st.kind = STEP_GEMM;
+                    st.in0 = cur;
+                    st.out = out_buf;
+                    GemmGeom& g = st.g;
+                    g.P = h * w; g.OW = w; g.Cin = c; g.TH = th; g.TW = tw; g.IH = h; g.IW = w;
+                    g.sy_o = 1; g.sy_t = -1; g.cy = (py + pad - ky0) / s;
+                    g.sx_o = 1; g.sx_t = -1; g.cx = (px + pad - kx0) / s;
+                    g.in_sample_stride = (int64_t)h * w * c;
+                    g.N = c_out; g.K = th * tw * c;
+                    g.OHf = oh; g.OWf = ow; g.osy = s; g.ooy = py; g.osx = s; g.oox = px;
+                    g.out_sample_stride = (int64_t)oh * ow * c_out;
+                    g.leaky = 1;
+                    std::vector<float> wkn((size_t)g.K * c_out);
+                    for (int jy = 0; jy < th; ++jy)
+                        for (int jx = 0; jx < tw; ++jx)
+                            for (int ci = 0; ci < c; ++ci)
+                                for (int co = 0; co < c_out; ++co) {
+                                    const int ky = ky0 + s * jy, kx = kx0 + s * jx;
+                                    wkn[((size_t)(jy * tw + jx) * c + ci) * c_out + co] =
+                                        wt[(((size_t)ky * k + kx) * c_out + co) * c + ci];
+                                }
+                    add_gemm_weights(net, st, wkn, bs);
+                    net.steps.push_back(st);
+                }
+            }
+            cur = out_buf;
+        }
+        h = oh; w = ow; c = c_out;
+    }
+    if (h != W || w != W) throw std::runtime_error("unexpected merger output map");
+}
+
+}  // namespace
+
+struct pnn_handle {
+    int device = 0;
+    float mean = 0.f;
+    int precision = PNN_PRECISION_BF16X3;
+    std::string error;
+    std::map<std::pair<int, int>, std::unique_ptr<Net>> nets;   // (width, is_fc)
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    size_t workspace_budget = (size_t)8 << 30;
+    // host-API staging
+    DevBuf d_images, d_idx, d_rows, d_cols, d_in0, d_in1;
+    // HM path
+    int32_t* hm_staged = nullptr;    // pinned, 5*64*64 ints
+    int32_t* hm_out = nullptr;       // pinned, 64*64 ints
+    DevBuf d_hm_staged;
+    int hm_width = 0;
+    uint32_t hm_mask_lo = 0, hm_mask_hi = 0;
+    int hm_unit_w = 4, hm_left_rows = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float hm_ms = 0.f;
+};
+
+namespace {
+
+Net* find_net(pnn_handle* h, int width, int is_fc) {
+    auto it = h->nets.find({width, is_fc ? 1 : 0});
+    if (it == h->nets.end()) {
+        throw std::runtime_error("no " + std::string(is_fc ? "fully-connected" : "convolutional") + " PNN of width " +
+                                 std::to_string(width) + " is loaded");
+    }
+    return it->second.get();
+}
+
+int64_t choose_capacity(pnn_handle* h, const Net& net, int64_t n) {
+    int64_t per = 0;
+    for (int64_t e : net.buf_elems) per += e * 6;
+    per += (int64_t)net.W * net.W * 9 + 8;
+    int64_t cap = std::max<int64_t>(1, (int64_t)(h->workspace_budget / (size_t)per));
+    // keep rows (cap * positions) comfortably inside int32
+    cap = std::min<int64_t>(cap, (int64_t)1 << 19);
+    return std::min(cap, std::max<int64_t>(n, 1));
+}
+
+void ensure_workspace(Net& net, int64_t cap) {
+    if (cap <= net.cap) return;
+    if (net.ws0.empty()) {
+        for (size_t i = 0; i < net.buf_elems.size(); ++i) {
+            net.ws0.emplace_back(new DevBuf());
+            net.ws1.emplace_back(new DevBuf());
+        }
+    }
+    for (size_t i = 0; i < net.buf_elems.size(); ++i) {
+        net.ws0[i]->reserve((size_t)cap * net.buf_elems[i] * 4);
+        if (!net.buf_fp32_only[i]) net.ws1[i]->reserve((size_t)cap * net.buf_elems[i] * 2);
+    }
+    const size_t px = (size_t)net.W * net.W;
+    net.out_raw.reserve(cap * px * 4);
+    net.out_u8.reserve(cap * px);
+    net.out_i32.reserve(cap * px * 4);
+    net.out_psnr.reserve(cap * 8);
+    net.cap = cap;
+}
+
+Act act_of(Net& net, int buf) {
+    Act a;
+    a.p0 = net.ws0[buf]->p;
+    a.p1 = net.ws1[buf]->p;
+    return a;
+}
+
+// Runs every layer of `net` on `n` samples whose contexts are already in the input buffers.
+void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream_t stream) {
+    const bool split = h->precision == PNN_PRECISION_BF16X3;
+    for (const Step& st : net.steps) {
+        switch (st.kind) {
+            case STEP_GEMM: {
+                GemmLaunch L{};
+                L.g = st.g;
+                L.in = act_of(net, st.in0);
+                if (st.is_final) {
+                    L.out_mode = OUT_FINAL;
+                    L.fin = fin;
+                } else {
+                    L.out_mode = OUT_ACT;
+                    L.out = act_of(net, st.out);
+                }
+                L.M = (int)(n * st.g.P);
+                L.w_fp32 = st.d_w32;
+                L.w_tiles = st.d_wt;
+                L.bias = st.d_bias;
+                h->launches += split ? launch_gemm_tc(L, stream) : launch_gemm_fp32(L, stream);
+                break;
+            }
+            case STEP_CONV0: {
+                Conv0Launch L{};
+                L.in = (const float*)net.ws0[st.in0]->p;
+                L.out = act_of(net, st.out);
+                L.w = st.d_w32;
+                L.bias = st.d_bias;
+                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.OH = st.OH; L.OW = st.OW; L.Cout = st.C;
+                L.k = st.k; L.stride = st.stride; L.pad = st.pad; L.split = split;
+                h->launches += launch_conv0(L, stream);
+                break;
+            }
+            case STEP_MERGER: {
+                MergerLaunch L{};
+                L.in0 = act_of(net, st.in0);
+                L.in1 = act_of(net, st.in1);
+                L.out = act_of(net, st.out);
+                L.w = st.d_w32;
+                L.bias = st.d_bias;
+                L.n = (int)n; L.C = st.C; L.split = split;
+                h->launches += launch_merger(L, stream);
+                break;
+            }
+            case STEP_TCONV_LAST: {
+                TconvLastLaunch L{};
+                L.in = act_of(net, st.in0);
+                L.w = st.d_w32;
+                L.bias = st.bias_scalar;
+                L.fin = fin;
+                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.Cin = st.C; L.k = st.k; L.stride = st.stride; L.pad = st.pad;
+                L.split = split;
+                h->launches += launch_tconv_last(L, stream);
+                break;
+            }
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+void check_masks(int W, int mask_w, int mask_h) {
+    // reference sets/common.py:444-447
+    if (mask_w < 0 || mask_w > W || mask_w % 4) throw std::runtime_error("`mask_w` does not belong to {0, 4, ..., width}");
+    if (mask_h < 0 || mask_h > W || mask_h % 4) throw std::runtime_error("`mask_h` does not belong to {0, 4, ..., width}");
+}
+
+// device-pointer core of the image-block path
+void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int H, int Wimg, const int32_t* d_idx,
+                         const int32_t* d_rows, const int32_t* d_cols, int64_t n, int mask_w, int mask_h, float* d_f32,
+                         uint8_t* d_u8, double* d_psnr, cudaStream_t stream) {
+    const int W = net.W;
+    const int64_t px = (int64_t)W * W;
+    const bool split = h->precision == PNN_PRECISION_BF16X3;
+    const int64_t cap = choose_capacity(h, net, n);
+    ensure_workspace(net, cap);
+    for (int64_t s0 = 0; s0 < n; s0 += cap) {
+        const int64_t m = std::min(cap, n - s0);
+        GatherLaunch G{};
+        G.images = d_images;
+        G.image_index = d_idx ? d_idx + s0 : nullptr;
+        G.rows = d_rows + s0;
+        G.cols = d_cols + s0;
+        G.n = m; G.H = H; G.Wimg = Wimg; G.W = W; G.mask_w = mask_w; G.mask_h = mask_h; G.mean = h->mean;
+        if (net.is_fc) {
+            // reference sets/common.py:467-472: flattened above then flattened left in one row
+            Act flat = act_of(net, net.in_above);
+            G.above = flat;
+            G.left = flat;
+            const int64_t shift = 3 * px;
+            if (split) {
+                G.left.p0 = (__nv_bfloat16*)flat.p0 + shift;
+                G.left.p1 = (__nv_bfloat16*)flat.p1 + shift;
+            } else {
+                G.left.p0 = (float*)flat.p0 + shift;
+            }
+            G.pitch_above = G.pitch_left = 5 * px;
+            G.split = split;
+        } else {
+            G.above = act_of(net, net.in_above);
+            G.left = act_of(net, net.in_left);
+            G.pitch_above = 3 * px;
+            G.pitch_left = 2 * px;
+            G.split = 0;
+        }
+        h->launches += launch_gather_image(G, stream);
+        FinalOut fin{};
+        fin.raw = d_f32 ? d_f32 + s0 * px : nullptr;
+        uint8_t* u8 = d_u8 ? d_u8 + s0 * px : (d_psnr ? (uint8_t*)net.out_u8.p : nullptr);
+        fin.u8 = u8;
+        fin.mean = h->mean;
+        fin.round_mode = PNN_ROUND_HALF_EVEN;
+        run_net(h, net, m, fin, stream);
+        if (d_psnr) {
+            h->launches += launch_psnr(d_images, G.image_index, G.rows, G.cols, m, H, Wimg, W, u8, d_psnr + s0, stream);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+}
+
+void batch_device(pnn_handle* h, Net& net, const float* d_a, const float* d_l, int64_t n, float* d_out, cudaStream_t stream) {
+    const int W = net.W;
+    const int64_t px = (int64_t)W * W;
+    const bool split = h->precision == PNN_PRECISION_BF16X3;
+    const int64_t cap = choose_capacity(h, net, n);
+    ensure_workspace(net, cap);
+    for (int64_t s0 = 0; s0 < n; s0 += cap) {
+        const int64_t m = std::min(cap, n - s0);
+        if (net.is_fc) {
+            h->launches += launch_convert_input(d_a + s0 * 5 * px, act_of(net, net.in_above), m * 5 * px, split, stream);
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(net.ws0[net.in_above]->p, d_a + s0 * 3 * px, (size_t)m * 3 * px * 4,
+                                     cudaMemcpyDeviceToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(net.ws0[net.in_left]->p, d_l + s0 * 2 * px, (size_t)m * 2 * px * 4,
+                                     cudaMemcpyDeviceToDevice, stream));
+        }
+        FinalOut fin{};
+        fin.raw = d_out + s0 * px;
+        fin.mean = h->mean;
+        run_net(h, net, m, fin, stream);
+    }
+}
+
+int fail(pnn_handle* h, const std::exception& e) {
+    if (h) h->error = e.what();
+    else g_create_error = e.what();
+    return -1;
+}
+
+void load_net_impl(pnn_handle* h, const std::string& path) {
+    FlatFile ff = read_flat(path);
+    std::unique_ptr<Net> net(new Net());
+    net->W = ff.width;
+    net->is_fc = ff.is_fc;
+    if (ff.width != 4 && ff.width != 8 && ff.width != 16 && ff.width != 32 && ff.width != 64) {
+        throw std::runtime_error("unsupported target width " + std::to_string(ff.width));
+    }
+    if (ff.is_fc) build_fc(*net, ff);
+    else build_conv(*net, ff);
+    h->nets[{ff.width, ff.is_fc ? 1 : 0}] = std::move(net);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pnn_version(void) { return "libpnn_cuda 0.1 (sm_100a)"; }
+
+int pnn_create(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out) {
+    if (!out) {
+        g_create_error = "`out` is NULL";
+        return -1;
+    }
+    *out = nullptr;
+    std::unique_ptr<pnn_handle> h(new pnn_handle());
+    try {
+        // reference TComPrediction.cpp(substitution):129-133
+        if (qp_selection <= 0) {
+            throw std::runtime_error("The quantization parameter used for selecting each prediction neural network model is not strictly positive.");
+        }
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) {
+            throw std::runtime_error(std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                     " (libpnn_cuda has no CPU fallback)");
+        }
+        if (device < 0 || device >= count) throw std::runtime_error("invalid CUDA device ordinal");
+        CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            throw std::runtime_error(std::string("device \"") + prop.name + "\" is not sm_100 (libpnn_cuda is built for sm_100a only)");
+        }
+        h->device = device;
+        h->mean = mean_training;
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&h->ev0));
+        CUDA_TRY(cudaEventCreate(&h->ev1));
+        CUDA_TRY(cudaMallocHost((void**)&h->hm_staged, 5 * 64 * 64 * sizeof(int32_t)));
+        CUDA_TRY(cudaMallocHost((void**)&h->hm_out, 64 * 64 * sizeof(int32_t)));
+        h->d_hm_staged.reserve(5 * 64 * 64 * sizeof(int32_t));
+        CUDA_TRY(gemm_tc_init());
+        if (paths_file && paths_file[0]) {
+            // reference hevc/hm_common/c++/source_common/tools.cpp:40-110 (parse_file_strings_three_keys):
+            // `width,is_pair,0,path`; "pair" models are used when listed and qp_selection >= 32
+            // (TComPrediction.cpp(substitution):156)
+            std::ifstream f(paths_file);
+            if (!f) throw std::runtime_error(std::string("The file at \"") + paths_file + "\" cannot be opened.");
+            std::map<int, std::string> single, pair;
+            std::string line;
+            while (std::getline(f, line)) {
+                if (line.find_first_not_of(" \t\f\v\n\r") == std::string::npos) continue;
+                std::vector<std::string> parts;
+                std::stringstream ss(line);
+                std::string item;
+                while (std::getline(ss, item, ',')) parts.push_back(item);
+                if (parts.size() < 4) throw std::runtime_error("malformed line in the paths file: \"" + line + "\"");
+                const int width = std::stoi(parts[0]);
+                const bool is_pair = std::stoi(parts[1]) != 0;
+                std::string p = parts[3];
+                p.erase(0, p.find_first_not_of(" \t\f\v\n\r"));
+                p.erase(p.find_last_not_of(" \t\f\v\n\r") + 1);
+                (is_pair ? pair : single)[width] = p;
+            }
+            const bool use_pair = !pair.empty() && qp_selection >= 32;
+            const std::map<int, std::string>& chosen = use_pair ? pair : single;
+            for (int width : {4, 8, 16, 32, 64}) {
+                auto it = chosen.find(width);
+                if (it == chosen.end()) throw std::runtime_error("the paths file has no entry for width " + std::to_string(width));
+                load_net_impl(h.get(), it->second);
+            }
+        }
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return -1;
+    }
+    *out = h.release();
+    return 0;
+}
+
+void pnn_destroy(pnn_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    h->nets.clear();
+    if (h->hm_staged) cudaFreeHost(h->hm_staged);
+    if (h->hm_out) cudaFreeHost(h->hm_out);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* pnn_last_error(pnn_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int pnn_load_net(pnn_handle* h, const char* path) {
+    if (!h) return -1;
+    try {
+        if (!path) throw std::runtime_error("`flat_binary_path` is NULL");
+        CUDA_TRY(cudaSetDevice(h->device));
+        load_net_impl(h, path);
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_set_precision(pnn_handle* h, int precision) {
+    if (!h) return -1;
+    if (precision != PNN_PRECISION_FP32 && precision != PNN_PRECISION_BF16X3) {
+        h->error = "unknown precision";
+        return -1;
+    }
+    h->precision = precision;
+    return 0;
+}
+
+int64_t pnn_launch_count(pnn_handle* h) { return h ? h->launches : 0; }
+
+float pnn_last_hm_device_ms(pnn_handle* h) { return h ? h->hm_ms : 0.f; }
+
+int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic_stride, const uint8_t* flags,
+                    int num_intra_neighbor, int unit_width, int unit_height, int above_units, int left_units) {
+    if (!h) return -1;
+    try {
+        // same checks and messages as reference extraction_context.cpp:17-47
+        if (!roi_origin) throw std::runtime_error("`piRoiOrigin` is NULL.");
+        if (!flags) throw std::runtime_error("`bNeighborFlags` is NULL.");
+        if (num_intra_neighbor <= 0) throw std::runtime_error("`iNumIntraNeighbor` is not strictly positive.");
+        if (width != 4 && width != 8 && width != 16 && width != 32 && width != 64) {
+            throw std::runtime_error("the width of the TB does not belong to {4, 8, 16, 32, 64}");
+        }
+        if (unit_width <= 0 || unit_height <= 0 || above_units <= 0 || left_units <= 0 || above_units > 64 ||
+            above_units * unit_width > 2 * width || left_units * unit_height > 2 * width) {
+            throw std::runtime_error("inconsistent neighbouring unit description");
+        }
+        const int W = width, cw = 3 * W;
+        int32_t* above = h->hm_staged;
+        int32_t* left = h->hm_staged + 3 * W * W;
+        const int total = above_units + left_units + 1;
+        uint32_t lo = 0, hi = 0;
+        int left_rows;
+        if (num_intra_neighbor == total) {
+            // extraction_context.cpp:56-90: straight copy
+            const int32_t* p = roi_origin - (int64_t)W * pic_stride - W;
+            for (int i = 0; i < W; ++i, p += pic_stride) memcpy(above + i * cw, p, cw * sizeof(int32_t));
+            p = roi_origin - W;
+            for (int i = 0; i < 2 * W; ++i, p += pic_stride) memcpy(left + i * W, p, W * sizeof(int32_t));
+            for (int u = 0; u < above_units; ++u) (u < 32 ? lo : hi) |= 1u << (u & 31);
+            left_rows = 2 * W;
+            // a unit grid that does not cover the whole portion leaves the rest to the straight copy
+            if (above_units * unit_width < 2 * W) {
+                for (int u = above_units; u * unit_width < 2 * W; ++u) (u < 32 ? lo : hi) |= 1u << (u & 31);
+            }
+        } else {
+            memset(h->hm_staged, 0, 5 * W * W * sizeof(int32_t));
+            // extraction_context.cpp:119-127: the W x W block above-left is always copied
+            const int32_t* p = roi_origin - (int64_t)W * pic_stride - W;
+            for (int i = 0; i < W; ++i, p += pic_stride) memcpy(above + i * cw, p, W * sizeof(int32_t));
+            // extraction_context.cpp:133-138
+            if (!flags[left_units]) {
+                throw std::runtime_error("The neighbouring unit above and on the left side of the current TB is not available.");
+            }
+            // extraction_context.cpp:149-166
+            for (int u = 0; u < above_units; ++u) {
+                if (!flags[left_units + 1 + u]) continue;
+                (u < 32 ? lo : hi) |= 1u << (u & 31);
+                const int32_t* q = roi_origin - (int64_t)W * pic_stride + u * unit_width;
+                int32_t* d = above + W + u * unit_width;
+                for (int j = 0; j < W; ++j, q += pic_stride, d += cw) memcpy(d, q, unit_width * sizeof(int32_t));
+            }
+            // extraction_context.cpp:189-205: source and destination advance only on available units
+            int n_left = 0;
+            for (int u = 0; u < left_units; ++u) n_left += flags[left_units - 1 - u] ? 1 : 0;
+            left_rows = n_left * unit_height;
+            p = roi_origin - W;
+            for (int i = 0; i < left_rows; ++i, p += pic_stride) memcpy(left + i * W, p, W * sizeof(int32_t));
+        }
+        h->hm_width = W;
+        h->hm_mask_lo = lo;
+        h->hm_mask_hi = hi;
+        h->hm_unit_w = unit_width;
+        h->hm_left_rows = left_rows;
+    } catch (const std::exception& e) {
+        h->hm_width = 0;
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
+    if (!h) return -1;
+    try {
+        if (!dst) throw std::runtime_error("`piPred` is NULL.");
+        if (h->hm_width != width) throw std::runtime_error("pnn_predict_hm called without a matching pnn_set_context");
+        CUDA_TRY(cudaSetDevice(h->device));
+        // reference TComPrediction.cpp(substitution):564: FC nets for widths 4 and 8, convolutional above
+        Net& net = *find_net(h, width, width <= 8);
+        const int W = width;
+        const bool split = h->precision == PNN_PRECISION_BF16X3;
+        ensure_workspace(net, 1);
+        cudaStream_t s = h->stream;
+        CUDA_TRY(cudaEventRecord(h->ev0, s));
+        CUDA_TRY(cudaMemcpyAsync(h->d_hm_staged.p, h->hm_staged, 5 * W * W * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        GatherHmLaunch G{};
+        G.staged = (const int32_t*)h->d_hm_staged.p;
+        G.W = W;
+        G.above_mask_lo = h->hm_mask_lo;
+        G.above_mask_hi = h->hm_mask_hi;
+        G.unit_w = h->hm_unit_w;
+        G.left_rows_valid = h->hm_left_rows;
+        G.mean = h->mean;
+        if (net.is_fc) {
+            Act flat = act_of(net, net.in_above);
+            G.above = flat;
+            G.left = flat;
+            if (split) {
+                G.left.p0 = (__nv_bfloat16*)flat.p0 + 3 * W * W;
+                G.left.p1 = (__nv_bfloat16*)flat.p1 + 3 * W * W;
+            } else {
+                G.left.p0 = (float*)flat.p0 + 3 * W * W;
+            }
+            G.split = split;
+        } else {
+            G.above = act_of(net, net.in_above);
+            G.left = act_of(net, net.in_left);
+            G.split = 0;
+        }
+        h->launches += launch_gather_hm(G, s);
+        FinalOut fin{};
+        fin.i32 = (int32_t*)net.out_i32.p;
+        fin.mean = h->mean;
+        fin.round_mode = PNN_ROUND_HALF_AWAY;
+        run_net(h, net, 1, fin, s);
+        CUDA_TRY(cudaMemcpyAsync(h->hm_out, net.out_i32.p, W * W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaEventRecord(h->ev1, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaEventElapsedTime(&h->hm_ms, h->ev0, h->ev1));
+        // reference TComPrediction.cpp(substitution):626-635: row-major copy with HM's stride
+        for (int i = 0; i < W; ++i) memcpy(dst + (int64_t)i * dst_stride, h->hm_out + i * W, W * sizeof(int32_t));
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_batch_device(pnn_handle* h, int width, int is_fc, const float* d_a, const float* d_l, int64_t n,
+                             float* d_out, void* stream) {
+    if (!h) return -1;
+    try {
+        if (n < 0) throw std::runtime_error("negative number of predictions");
+        if (!d_a || !d_out || (!is_fc && !d_l)) throw std::runtime_error("NULL buffer");
+        CUDA_TRY(cudaSetDevice(h->device));
+        batch_device(h, *find_net(h, width, is_fc), d_a, d_l, n, d_out, (cudaStream_t)stream);
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_batch(pnn_handle* h, int width, int is_fc, const float* a, const float* l, int64_t n, float* out) {
+    if (!h) return -1;
+    try {
+        if (n < 0) throw std::runtime_error("negative number of predictions");
+        if (n == 0) return 0;
+        if (!a || !out || (!is_fc && !l)) throw std::runtime_error("NULL buffer");
+        CUDA_TRY(cudaSetDevice(h->device));
+        Net& net = *find_net(h, width, is_fc);
+        const int64_t px = (int64_t)width * width;
+        const int64_t na = is_fc ? 5 * px : 3 * px;
+        // chunk so that the staging buffers stay bounded
+        const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1, ((int64_t)1 << 28) / (5 * px * 4)));
+        h->d_in0.reserve((size_t)chunk * na * 4);
+        if (!is_fc) h->d_in1.reserve((size_t)chunk * 2 * px * 4);
+        ensure_workspace(net, choose_capacity(h, net, chunk));
+        DevBuf& d_out = net.out_raw;
+        d_out.reserve((size_t)chunk * px * 4);
+        for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+            const int64_t m = std::min(chunk, n - s0);
+            CUDA_TRY(cudaMemcpyAsync(h->d_in0.p, a + s0 * na, (size_t)m * na * 4, cudaMemcpyHostToDevice, h->stream));
+            if (!is_fc) {
+                CUDA_TRY(cudaMemcpyAsync(h->d_in1.p, l + s0 * 2 * px, (size_t)m * 2 * px * 4, cudaMemcpyHostToDevice, h->stream));
+            }
+            batch_device(h, net, (const float*)h->d_in0.p, (const float*)h->d_in1.p, m, (float*)d_out.p, h->stream);
+            CUDA_TRY(cudaMemcpyAsync(out + s0 * px, d_out.p, (size_t)m * px * 4, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+        }
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_image_blocks_device(pnn_handle* h, int width, int is_fc, const uint8_t* d_images, int n_images,
+                                    int height, int width_image, const int32_t* d_idx, const int32_t* d_rows,
+                                    const int32_t* d_cols, int64_t n, int mask_w, int mask_h, float* d_f32,
+                                    uint8_t* d_u8, double* d_psnr, void* stream) {
+    if (!h) return -1;
+    try {
+        if (n < 0) throw std::runtime_error("negative number of predictions");
+        if (!d_images || !d_rows || !d_cols) throw std::runtime_error("NULL buffer");
+        if (n_images > 1 && !d_idx) throw std::runtime_error("`image_index` is NULL while there are several images");
+        check_masks(width, mask_w, mask_h);
+        CUDA_TRY(cudaSetDevice(h->device));
+        image_blocks_device(h, *find_net(h, width, is_fc), d_images, height, width_image, d_idx, d_rows, d_cols, n, mask_w,
+                            mask_h, d_f32, d_u8, d_psnr, (cudaStream_t)stream);
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_image_blocks(pnn_handle* h, int width, int is_fc, const uint8_t* images, int n_images, int height,
+                             int width_image, const int32_t* idx, const int32_t* rows, const int32_t* cols, int64_t n,
+                             int mask_w, int mask_h, float* out_f32, uint8_t* out_u8, double* out_psnr) {
+    if (!h) return -1;
+    try {
+        if (n < 0) throw std::runtime_error("negative number of predictions");
+        if (!images || !rows || !cols) throw std::runtime_error("NULL buffer");
+        if (n_images > 1 && !idx) throw std::runtime_error("`image_index` is NULL while there are several images");
+        if (n_images <= 0 || height <= 0 || width_image <= 0) throw std::runtime_error("empty image set");
+        check_masks(width, mask_w, mask_h);
+        for (int64_t i = 0; i < n; ++i) {
+            // the target block and its above-left context anchor must lie inside the image
+            // (reference sets/common.py:82-91 raises for windows leaving the image; here only the
+            // above-right / below-left parts may leave it, and they are masked)
+            if (rows[i] < width || cols[i] < width || rows[i] + width > height || cols[i] + width > width_image) {
+                throw std::runtime_error("block " + std::to_string(i) + " or its context anchor lies outside the image");
+            }
+            if (idx && (idx[i] < 0 || idx[i] >= n_images)) throw std::runtime_error("`image_index` out of range");
+        }
+        if (n == 0) return 0;
+        CUDA_TRY(cudaSetDevice(h->device));
+        Net& net = *find_net(h, width, is_fc);
+        const int64_t px = (int64_t)width * width;
+        cudaStream_t s = h->stream;
+        const size_t img_bytes = (size_t)n_images * height * width_image;
+        h->d_images.reserve(img_bytes);
+        h->d_rows.reserve(n * 4);
+        h->d_cols.reserve(n * 4);
+        if (idx) h->d_idx.reserve(n * 4);
+        CUDA_TRY(cudaMemcpyAsync(h->d_images.p, images, img_bytes, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->d_rows.p, rows, n * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->d_cols.p, cols, n * 4, cudaMemcpyHostToDevice, s));
+        if (idx) CUDA_TRY(cudaMemcpyAsync(h->d_idx.p, idx, n * 4, cudaMemcpyHostToDevice, s));
+        // outputs are produced chunk by chunk into the net's own output buffers
+        const int64_t cap = choose_capacity(h, net, n);
+        ensure_workspace(net, cap);
+        for (int64_t s0 = 0; s0 < n; s0 += cap) {
+            const int64_t m = std::min(cap, n - s0);
+            image_blocks_device(h, net, (const uint8_t*)h->d_images.p, height, width_image,
+                                idx ? (const int32_t*)h->d_idx.p + s0 : nullptr, (const int32_t*)h->d_rows.p + s0,
+                                (const int32_t*)h->d_cols.p + s0, m, mask_w, mask_h,
+                                out_f32 ? (float*)net.out_raw.p : nullptr,
+                                (out_u8 || out_psnr) ? (uint8_t*)net.out_u8.p : nullptr,
+                                out_psnr ? (double*)net.out_psnr.p : nullptr, s);
+            if (out_f32) CUDA_TRY(cudaMemcpyAsync(out_f32 + s0 * px, net.out_raw.p, (size_t)m * px * 4, cudaMemcpyDeviceToHost, s));
+            if (out_u8) CUDA_TRY(cudaMemcpyAsync(out_u8 + s0 * px, net.out_u8.p, (size_t)m * px, cudaMemcpyDeviceToHost, s));
+            if (out_psnr) CUDA_TRY(cudaMemcpyAsync(out_psnr + s0, net.out_psnr.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+}  // extern "C"

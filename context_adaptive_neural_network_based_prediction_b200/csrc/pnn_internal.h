@@ -1,0 +1,166 @@
+// Internal declarations shared by the host side and the kernels of libpnn_cuda.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace pnn {
+
+// ---------------------------------------------------------------------------------------------
+// Activation storage.  fp32 precision: p0 = float*.  bf16x3 precision: p0 = hi plane, p1 = lo plane
+// (__nv_bfloat16*), value = hi + lo.  Layout is always [sample][pixel][channel] (NHWC), exact pitches.
+// ---------------------------------------------------------------------------------------------
+struct Act {
+    void* p0;
+    void* p1;
+};
+
+// Output conversion of a layer.
+enum OutMode {
+    OUT_ACT = 0,    // next layer's input (fp32 or split planes depending on precision)
+    OUT_FINAL = 1   // network output: raw fp32 (+ optional rounded u8 / int32), see FinalOut
+};
+
+struct FinalOut {
+    float* raw;        // [n, W*W] prediction before the mean is added back (may be null)
+    uint8_t* u8;       // [n, W*W] round(clip(p + mean, 0, 255)) (may be null)
+    int32_t* i32;      // same as int32 (HM's Pel) (may be null)
+    float mean;
+    int round_mode;    // PNN_ROUND_*
+};
+
+// Geometry of one GEMM-shaped layer (FC, convolution, or one phase of a transposed convolution):
+//   out[b, oy*osy+ooy, ox*osx+oox, n] = act( sum_{ty,tx,ci} in[b, oy*sy_o+ty*sy_t+cy, ox*sx_o+tx*sx_t+cx, ci]
+//                                                         * Wm[(ty*TW+tx)*Cin+ci, n] + bias[n] )
+// rows m = b*P + oy*OW + ox.  Out-of-range input pixels read as zero (SAME padding / tconv borders).
+struct GemmGeom {
+    int P, OW;                  // output positions per sample in this launch, and their row width
+    int Cin, TH, TW;            // K = TH*TW*Cin
+    int IH, IW;                 // input map
+    int sy_o, sy_t, cy;
+    int sx_o, sx_t, cx;
+    int64_t in_sample_stride;   // elements
+    int N, K;
+    int OHf, OWf;               // full output map (for the output address)
+    int osy, ooy, osx, oox;
+    int64_t out_sample_stride;  // elements
+    int leaky;                  // 1: LeakyReLU(0.1), 0: linear
+};
+
+struct GemmLaunch {
+    GemmGeom g;
+    Act in;
+    Act out;                    // OUT_ACT
+    FinalOut fin;               // OUT_FINAL
+    int out_mode;
+    int M;                      // rows in this launch
+    const float* w_fp32;        // [K][N] fp32 (fp32 precision)
+    const uint8_t* w_tiles;     // pre-swizzled bf16 hi/lo tiles (bf16x3 precision)
+    const float* bias;          // [N]
+};
+
+// bf16x3 weight tiling (see DESIGN.md "weight tiles"): N is cut in tiles of TC_BN rows (the last one
+// narrower, a multiple of 16), K in blocks of 64.  Tile (nt, kb) is stored as the exact shared-memory
+// image of its hi plane followed by its lo plane, 128-byte-swizzled K-major, so that one bulk copy
+// lands it ready for tcgen05.mma.
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 256;
+constexpr int TC_BK = 64;
+
+inline int tc_num_kb(int K) { return (K + TC_BK - 1) / TC_BK; }
+inline int tc_num_nt(int N) { return (N + TC_BN - 1) / TC_BN; }
+inline int tc_tile_bn(int N, int nt) {
+    int rem = N - nt * TC_BN;
+    if (rem > TC_BN) rem = TC_BN;
+    return (rem + 15) / 16 * 16;
+}
+// byte offset of tile (nt, kb)
+inline size_t tc_tile_offset(int N, int K, int nt, int kb) {
+    size_t off = 0;
+    for (int t = 0; t < nt; ++t) off += (size_t)tc_num_kb(K) * 2 * tc_tile_bn(N, t) * 128;
+    return off + (size_t)kb * 2 * tc_tile_bn(N, nt) * 128;
+}
+inline size_t tc_total_bytes(int N, int K) { return tc_tile_offset(N, K, tc_num_nt(N), 0); }
+
+// ---------------------------------------------------------------------------------------------
+// Kernel launchers (implemented in the .cu files).  All asynchronous on `stream`.
+// Each returns the number of kernels it launched.
+// ---------------------------------------------------------------------------------------------
+int launch_gemm_fp32(const GemmLaunch& L, cudaStream_t stream);
+int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);
+// one-time opt-in for the tcgen05 kernel's dynamic shared memory
+cudaError_t gemm_tc_init();
+
+// First convolution of a branch (one input channel, reference pnn/components.py:33-46 with i == 0).
+struct Conv0Launch {
+    const float* in;     // [n, IH, IW] fp32 context portion
+    Act out;             // [n, OH, OW, Cout]
+    const float* w;      // [k*k][Cout]
+    const float* bias;
+    int n, IH, IW, OH, OW, Cout, k, stride, pad;
+    int split;           // 1: write hi/lo bf16 planes
+};
+int launch_conv0(const Conv0Launch& L, cudaStream_t stream);
+
+// Channel-wise fully-connected merger (reference pnn/tfutils.py:8-73) + LeakyReLU.
+struct MergerLaunch {
+    Act in0, in1;        // [n, 48, C], [n, 32, C]
+    Act out;             // [n, 16, C]
+    const float* w;      // transposed on the host to [80][16][C]
+    const float* bias;   // [16][C]
+    int n, C, split;
+};
+int launch_merger(const MergerLaunch& L, cudaStream_t stream);
+
+// Last transposed convolution (one output channel, linear) with the fused epilogue.
+struct TconvLastLaunch {
+    Act in;              // [n, IH, IW, Cin]
+    const float* w;      // [k*k][Cin]  (w_tf[ky][kx][0][ci])
+    float bias;
+    FinalOut fin;
+    int n, IH, IW, Cin, k, stride, pad, split;
+};
+int launch_tconv_last(const TconvLastLaunch& L, cudaStream_t stream);
+
+// Fused gather: uint8 image -> mean-centred, masked context (reference sets/common.py:99-109, 454-472).
+struct GatherLaunch {
+    const uint8_t* images;      // [n_images, H, Wimg]
+    const int32_t* image_index; // may be null
+    const int32_t* rows;
+    const int32_t* cols;
+    int64_t n;
+    int H, Wimg, W, mask_w, mask_h;
+    float mean;
+    // destination of the above portion [n][W*3W] and of the left portion [n][2W*W]; `pitch_*` in elements
+    Act above, left;
+    int64_t pitch_above, pitch_left;
+    int split;
+};
+int launch_gather_image(const GatherLaunch& L, cudaStream_t stream);
+
+// HM gather: staged int32 context -> masked, mean-centred (reference extraction_context.cpp:56-205).
+struct GatherHmLaunch {
+    const int32_t* staged;      // [W*3W] above rows then [2W*W] left rows, raw reconstruction pixels
+    int W;
+    uint32_t above_mask_lo, above_mask_hi;  // bit i: above/above-right unit i available (units of unit_w columns)
+    int unit_w;
+    int left_rows_valid;        // rows of the left portion that are copied (rest stay zero)
+    float mean;
+    Act above, left;
+    int split;
+};
+int launch_gather_hm(const GatherHmLaunch& L, cudaStream_t stream);
+
+// fp32 -> (fp32 copy | split planes)
+int launch_convert_input(const float* src, Act dst, int64_t n_elems, int split, cudaStream_t stream);
+
+// PSNR of each block against its target in the image (reference tools/tools.py:364-401).
+int launch_psnr(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols,
+                int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream);
+
+}  // namespace pnn

@@ -1,0 +1,154 @@
+"""Python host side over the C ABI of libpnn_cuda (numpy in, numpy out; device-pointer variants for torch)."""
+import ctypes
+
+import numpy
+
+from . import _lib
+
+MEAN_TRAINING_LUMINANCE = 117.8952234192841   # reference sets/results/training_set/means/luminance/mean_training.pkl
+
+
+class PnnError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine(object):
+    """One `pnn_handle`: the nets loaded on one GPU.
+
+    Replaces the TensorFlow session(s) of the reference: `tf.Session` + `Saver.restore` on the
+    Python side (pnn/PredictionNeuralNetwork.py:185-200) and the five `tensorflow::Session`s of
+    HM (TComPrediction.cpp:108-236).
+    """
+
+    def __init__(self, mean_training=MEAN_TRAINING_LUMINANCE, device=0, paths_file=None, qp_selection=22):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self.mean_training = float(mean_training)
+        path = paths_file.encode() if paths_file else None
+        if self._lib.pnn_create(path, ctypes.c_float(self.mean_training), int(qp_selection), int(device),
+                                ctypes.byref(self._h)) != 0:
+            raise PnnError(self._lib.pnn_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, '_h', None) and self._h.value:
+            self._lib.pnn_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code):
+        if code != 0:
+            raise PnnError(self._lib.pnn_last_error(self._h).decode())
+
+    # ------------------------------------------------------------------ set-up
+    def load_net(self, path):
+        self._check(self._lib.pnn_load_net(self._h, path.encode()))
+
+    def set_precision(self, precision):
+        """'fp32' (FFMA yard-stick) or 'bf16x3' (tcgen05, default)."""
+        code = {'fp32': _lib.PRECISION_FP32, 'bf16x3': _lib.PRECISION_BF16X3}[precision]
+        self._check(self._lib.pnn_set_precision(self._h, code))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.pnn_launch_count(self._h))
+
+    @property
+    def last_hm_device_ms(self):
+        return float(self._lib.pnn_last_hm_device_ms(self._h))
+
+    # ------------------------------------------------------------------ offline path, host buffers
+    def predict_batch(self, width_target, is_fully_connected, above_or_flat, left=None):
+        """pnn.batching.predict_by_batch_via_pnn equivalent: float32 contexts -> float32 [N, W, W, 1]."""
+        a = numpy.ascontiguousarray(above_or_flat, dtype=numpy.float32)
+        n = a.shape[0]
+        px = width_target * width_target
+        if is_fully_connected:
+            if a.size != n * 5 * px:
+                raise ValueError('the flattened contexts must have shape [N, 5*W*W]')
+            l = None
+        else:
+            l = numpy.ascontiguousarray(left, dtype=numpy.float32)
+            if a.size != n * 3 * px or l.size != n * 2 * px:
+                raise ValueError('the context portions must have shapes [N, W, 3W, 1] and [N, 2W, W, 1]')
+        out = numpy.empty((n, width_target, width_target, 1), dtype=numpy.float32)
+        self._check(self._lib.pnn_predict_batch(self._h, width_target, int(bool(is_fully_connected)), _ptr(a), _ptr(l),
+                                                n, _ptr(out)))
+        return out
+
+    def predict_image_blocks(self, width_target, is_fully_connected, images_uint8, rows, cols, image_index=None,
+                             masks=(0, 0), want_float=True, want_uint8=True, want_psnr=True):
+        """Fused gather + net + epilogue for blocks of uint8 images [n_images, H, W_img] (or [H, W_img]).
+
+        Returns a dict with 'predictions_float32' [N, W, W] (raw), 'predictions_uint8' [N, W, W] and
+        'psnrs' [N] (float64) for the requested outputs.
+        """
+        img = numpy.ascontiguousarray(images_uint8, dtype=numpy.uint8)
+        if img.ndim == 2:
+            img = img[None]
+        rows = numpy.ascontiguousarray(rows, dtype=numpy.int32)
+        cols = numpy.ascontiguousarray(cols, dtype=numpy.int32)
+        n = rows.shape[0]
+        idx = None if image_index is None else numpy.ascontiguousarray(image_index, dtype=numpy.int32)
+        w = width_target
+        f32 = numpy.empty((n, w, w), dtype=numpy.float32) if want_float else None
+        u8 = numpy.empty((n, w, w), dtype=numpy.uint8) if want_uint8 else None
+        psnr = numpy.empty((n,), dtype=numpy.float64) if want_psnr else None
+        self._check(self._lib.pnn_predict_image_blocks(
+            self._h, w, int(bool(is_fully_connected)), _ptr(img), img.shape[0], img.shape[1], img.shape[2],
+            _ptr(idx), _ptr(rows), _ptr(cols), n, int(masks[0]), int(masks[1]), _ptr(f32), _ptr(u8), _ptr(psnr)))
+        out = {}
+        if want_float:
+            out['predictions_float32'] = f32
+        if want_uint8:
+            out['predictions_uint8'] = u8
+        if want_psnr:
+            out['psnrs'] = psnr
+        return out
+
+    # ------------------------------------------------------------------ offline path, device buffers
+    def predict_image_blocks_device(self, width_target, is_fully_connected, d_images, n_images, height, width_image,
+                                    d_image_index, d_rows, d_cols, n, masks, d_out_f32, d_out_u8, d_out_psnr,
+                                    stream=0):
+        """All pointers are integers (e.g. torch.Tensor.data_ptr()); asynchronous on `stream`."""
+        self._check(self._lib.pnn_predict_image_blocks_device(
+            self._h, width_target, int(bool(is_fully_connected)), d_images, n_images, height, width_image,
+            d_image_index, d_rows, d_cols, n, int(masks[0]), int(masks[1]), d_out_f32, d_out_u8, d_out_psnr,
+            stream))
+
+    def predict_batch_device(self, width_target, is_fully_connected, d_above_or_flat, d_left, n, d_out, stream=0):
+        self._check(self._lib.pnn_predict_batch_device(self._h, width_target, int(bool(is_fully_connected)),
+                                                       d_above_or_flat, d_left, n, d_out, stream))
+
+    # ------------------------------------------------------------------ in-loop (HM) path
+    def set_context(self, width, plane_int32, origin_row, origin_col, neighbor_flags, num_intra_neighbor,
+                    unit_width=4, unit_height=4, above_units=None, left_units=None):
+        """Mirrors extract_context_portions (reference extraction_context.h:36-48) on a numpy int32 plane."""
+        plane = plane_int32
+        if plane.dtype != numpy.int32 or not plane.flags['C_CONTIGUOUS'] or plane.ndim != 2:
+            raise ValueError('`plane_int32` must be a C-contiguous 2D int32 array')
+        stride = plane.shape[1]
+        if above_units is None:
+            above_units = 2 * width // unit_width
+        if left_units is None:
+            left_units = 2 * width // unit_height
+        flags = numpy.ascontiguousarray(neighbor_flags, dtype=numpy.uint8)
+        origin = plane.ctypes.data + 4 * (origin_row * stride + origin_col)
+        self._keep = (plane, flags)
+        self._check(self._lib.pnn_set_context(self._h, width, ctypes.c_void_p(origin), stride, _ptr(flags),
+                                              int(num_intra_neighbor), unit_width, unit_height, above_units, left_units))
+
+    def predict_hm(self, width, dst_stride=None):
+        """NN branch of predIntraAng: returns the int32 [W, W] prediction (HM rounding)."""
+        stride = width if dst_stride is None else dst_stride
+        dst = numpy.zeros((width, stride), dtype=numpy.int32)
+        self._check(self._lib.pnn_predict_hm(self._h, width, _ptr(dst), stride))
+        return dst[:, :width]

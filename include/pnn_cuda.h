@@ -1,0 +1,141 @@
+/*
+ * libpnn_cuda -- C ABI of the B200-native prediction-neural-network (PNN) engine.
+ *
+ * Drop-in boundary for the PNN forward pass of
+ * thierrydumas/context_adaptive_neural_network_based_prediction.  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference root).
+ * Plain pointers and sizes only; no torch / TensorFlow types.  All functions return
+ * 0 on success and -1 on error (the reference's hm_common convention,
+ * hevc/hm_common/c++/source_common/extraction_context.cpp:17-47); the message is
+ * available from pnn_last_error().  A handle is NOT thread-safe (the reference keeps
+ * one TComPrediction per HM process).
+ *
+ * There is no CPU fallback: pnn_create fails when no sm_100 device is present.
+ */
+#ifndef PNN_CUDA_H
+#define PNN_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pnn_handle pnn_handle;
+
+/* Arithmetic used by the GEMM-shaped layers. */
+enum {
+    PNN_PRECISION_FP32 = 0,    /* fp32 FFMA kernels: the accuracy yard-stick                       */
+    PNN_PRECISION_BF16X3 = 1   /* tcgen05 tensor cores, operands split hi/lo bf16, 3 MMAs, fp32 acc */
+};
+
+/* Output rounding of the fused epilogue. */
+enum {
+    PNN_ROUND_HALF_EVEN = 0,   /* numpy.round, reference tools/tools.py:49                         */
+    PNN_ROUND_HALF_AWAY = 1    /* std::round, reference TComPrediction.cpp(substitution):632       */
+};
+
+/*
+ * Replaces TComPrediction::initTempBuff's network set-up
+ * (hevc/hm_16_15_substitution/source/Lib/TLibCommon/TComPrediction.cpp:108-236) and
+ * load_graphs (hevc/hm_common/c++/source_common/integration_prediction_neural_network.cpp:29-69).
+ *
+ * `paths_file` is the reference's "paths to graphs" file (lines `width,is_pair,0,path`, e.g.
+ * hevc/hm_common/paths_to_graphs_output/pair.txt) whose paths now name PNNW flat binaries instead
+ * of frozen .pbtxt graphs; it may be NULL, in which case nets are added with pnn_load_net.
+ * `qp_selection` selects the "pair" models when it is >= 32 and the file lists pair entries
+ * (TComPrediction.cpp:156); it must be > 0 (TComPrediction.cpp:129-133).
+ * `mean_training` is the training-set mean (TComPrediction.cpp:219), `device` the CUDA ordinal.
+ */
+int pnn_create(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out);
+
+/* Replaces std::unique_ptr<tensorflow::Session> teardown. */
+void pnn_destroy(pnn_handle* h);
+
+/* Last error message of the handle (or of the failed pnn_create when h is NULL). */
+const char* pnn_last_error(pnn_handle* h);
+
+/*
+ * Loads one PNNW flat binary (width and type are read from its header) -- replaces one
+ * load_graph call (integration_prediction_neural_network.cpp:29-54) /
+ * PredictionNeuralNetwork.initialization (pnn/PredictionNeuralNetwork.py:185-200).
+ */
+int pnn_load_net(pnn_handle* h, const char* flat_binary_path);
+
+/* PNN_PRECISION_*; default PNN_PRECISION_BF16X3. */
+int pnn_set_precision(pnn_handle* h, int precision);
+
+/*
+ * Step 1 of the in-loop call: mirrors extract_context_portions
+ * (hevc/hm_common/c++/source_common/extraction_context.h:36-48, called from
+ * TComPattern.cpp(substitution):366-380).  `roi_origin` points at the top-left pixel of the
+ * current TB in HM's int reconstruction plane (row stride `pic_stride`); `neighbor_flags` holds
+ * left_units + above_units + 1 availability flags ordered bottom-left -> top-left, above-left,
+ * above -> above-right (TComPattern.cpp:260-280).  The context pixels are staged; masking and
+ * mean subtraction run on the device inside pnn_predict_hm.  A second call overwrites the first.
+ */
+int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic_stride,
+                    const uint8_t* neighbor_flags, int num_intra_neighbor,
+                    int unit_width, int unit_height, int above_units, int left_units);
+
+/*
+ * Step 2 of the in-loop call: the neural-network branch of TComPrediction::predIntraAng
+ * (TComPrediction.cpp(substitution):556-635): runs the net selected by `width` on the staged
+ * context and writes (int)std::round(clip(p + mean, 0, 255)) into dst[row*dst_stride + col].
+ * Synchronous: dst is complete on return.
+ */
+int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride);
+
+/*
+ * Offline path with already pre-processed contexts: pnn.batching.predict_by_batch_via_pnn
+ * (pnn/batching.py:7-88).  FC nets: `above_or_flat` is [n, 5*W*W], `left` is NULL.
+ * Conv nets: `above_or_flat` is [n, W, 3W, 1] and `left` is [n, 2W, W, 1].  `out` receives the raw
+ * float32 predictions [n, W, W, 1] (mean not added, like sess.run).  HOST pointers.
+ */
+int pnn_predict_batch(pnn_handle* h, int width, int is_fully_connected,
+                      const float* above_or_flat, const float* left, int64_t n, float* out);
+
+/*
+ * Offline path with the gather fused on the device: replaces
+ * extract_context_portions_targets_from_channel_numpy + preprocess_context_portions_targets_numpy
+ * (sets/common.py:13-263, 351-475), predict_by_batch_via_pnn and cast_float_to_uint8
+ * (tools/tools.py:17-49) for blocks of `n_images` uint8 images [n_images, height, width_image].
+ * Block i is the W x W target whose top-left pixel is (rows[i], cols[i]) of image image_index[i]
+ * (image_index may be NULL when n_images == 1).  mask_w / mask_h in {0,4,...,W} as in
+ * sets/common.py:444-447; context pixels outside the image are masked too.
+ * Outputs (each may be NULL): out_f32 raw predictions [n, W*W]; out_u8 =
+ * round_half_even(clip(p + mean, 0, 255)) [n, W*W]; out_psnr[n] = PSNR (float64, tools/tools.py:364-401)
+ * between the target block and out_u8.  HOST pointers.
+ */
+int pnn_predict_image_blocks(pnn_handle* h, int width, int is_fully_connected,
+                             const uint8_t* images, int n_images, int height, int width_image,
+                             const int32_t* image_index, const int32_t* rows, const int32_t* cols, int64_t n,
+                             int mask_w, int mask_h, float* out_f32, uint8_t* out_u8, double* out_psnr);
+
+/*
+ * Same two calls with DEVICE pointers, asynchronous on `cuda_stream` (a cudaStream_t, may be 0).
+ * These are what the throughput numbers with inputs resident in HBM are measured on.
+ */
+int pnn_predict_batch_device(pnn_handle* h, int width, int is_fully_connected,
+                             const float* d_above_or_flat, const float* d_left, int64_t n, float* d_out,
+                             void* cuda_stream);
+int pnn_predict_image_blocks_device(pnn_handle* h, int width, int is_fully_connected,
+                                    const uint8_t* d_images, int n_images, int height, int width_image,
+                                    const int32_t* d_image_index, const int32_t* d_rows, const int32_t* d_cols,
+                                    int64_t n, int mask_w, int mask_h,
+                                    float* d_out_f32, uint8_t* d_out_u8, double* d_out_psnr, void* cuda_stream);
+
+/* Kernels launched by this handle since creation (bench.py's gpu_launches). */
+int64_t pnn_launch_count(pnn_handle* h);
+
+/* Device time (ms, CUDA events on the handle's stream) of the last pnn_predict_hm call. */
+float pnn_last_hm_device_ms(pnn_handle* h);
+
+/* Library version string. */
+const char* pnn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PNN_CUDA_H */

@@ -1,0 +1,75 @@
+"""GPU tests of the in-loop (HM) call pair pnn_set_context / pnn_predict_hm against the oracle."""
+import numpy
+import pytest
+
+import helpers
+from helpers import MEAN
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_hm(wts, width, plane, orow, ocol, flags, n_avail):
+    from oracle import context, epilogue, nets
+    stride = plane.shape[1]
+    units = 2 * width // 4
+    code, above, left = context.extract_context_portions_hm(plane.ravel(), stride, orow * stride + ocol, flags, n_avail, 4, 4,
+                                                            units, units, width, MEAN)
+    assert code == 0
+    is_fc = width <= 8
+    if is_fc:
+        pred = nets.forward_fc(wts, numpy.concatenate([above, left])[None])
+    else:
+        pred = nets.forward_conv(wts, above.reshape(1, width, 3 * width, 1), left.reshape(1, 2 * width, width, 1))
+    return pred[0, :, :, 0], epilogue.epilogue_hm(pred[0, :, :, 0], MEAN)
+
+
+@pytest.mark.parametrize('width', [4, 8, 16, 32, 64])
+def test_hm_call_pair(engine, weights_dir, width):
+    """Net selection by width as TComPrediction.cpp:564; availability patterns as TComPattern.cpp:260-280."""
+    is_fc = width <= 8
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=40 + width, gain=1.6 if is_fc else 1.25)
+    engine.load_net(path)
+    engine.set_precision('bf16x3')
+    plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 5).astype(numpy.int32)
+    orow, ocol = width + 3, width + 5
+    units = 2 * width // 4
+    patterns = []
+    full = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+    patterns.append(full)
+    p = full.copy(); p[:units // 2] = 0; patterns.append(p)                    # below-left unavailable
+    p = full.copy(); p[units + 1 + units // 2:] = 0; patterns.append(p)        # above-right unavailable
+    p = full.copy(); p[:units // 2] = 0; p[units + 1 + units // 2:] = 0; patterns.append(p)
+    p = full.copy(); p[:units] = 0; p[units + 1:] = 0; patterns.append(p)       # only above-left
+    total_px, same_px = 0, 0
+    for flags in patterns:
+        n_avail = int(flags.sum())
+        engine.set_context(width, plane, orow, ocol, flags, n_avail)
+        got = engine.predict_hm(width, dst_stride=width + 5)
+        again = engine.predict_hm(width)
+        numpy.testing.assert_array_equal(got, again)                           # same bits on every call
+        _, want = _oracle_hm(wts, width, plane, orow, ocol, flags, n_avail)
+        assert numpy.abs(got - want).max() <= 1
+        total_px += want.size
+        same_px += int((got == want).sum())
+        assert got.min() >= 0 and got.max() <= 255
+    assert same_px >= 0.999 * total_px
+
+
+def test_hm_error_behaviour(engine, weights_dir):
+    """Same -1 conditions as extraction_context.cpp:17-47 and :133-138."""
+    from context_adaptive_neural_network_based_prediction_b200 import PnnError
+    path, _ = helpers.make_net_file(weights_dir, 8, True, seed=48)
+    engine.load_net(path)
+    plane = helpers.synthetic_image(40, 48, 1).astype(numpy.int32)
+    flags = numpy.ones(9, dtype=numpy.uint8)
+    with pytest.raises(PnnError):
+        engine.set_context(8, plane, 11, 13, flags, 0)                          # iNumIntraNeighbor <= 0
+    flags[4] = 0
+    with pytest.raises(PnnError):
+        engine.set_context(8, plane, 11, 13, flags, 8)                          # above-left unavailable
+    with pytest.raises(PnnError):
+        engine.predict_hm(8)                                                    # no staged context
+    flags[4] = 1
+    engine.set_context(8, plane, 11, 13, flags, 9)
+    with pytest.raises(PnnError):
+        engine.predict_hm(16)                                                   # width mismatch
