@@ -14,7 +14,7 @@ EXPORTS = (
     'pnn_create', 'pnn_destroy', 'pnn_last_error', 'pnn_load_net', 'pnn_set_precision',
     'pnn_set_context', 'pnn_predict_hm', 'pnn_predict_batch', 'pnn_predict_image_blocks',
     'pnn_predict_batch_device', 'pnn_predict_image_blocks_device', 'pnn_launch_count',
-    'pnn_last_hm_device_ms', 'pnn_version',
+    'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation',
 )
 
 PRECISION_FP32 = 0
@@ -61,6 +61,8 @@ def load():
     lib.pnn_launch_count.restype = i64
     lib.pnn_last_hm_device_ms.argtypes = [vp]
     lib.pnn_last_hm_device_ms.restype = c.c_float
+    lib.pnn_debug_get_activation.argtypes = [vp, i32, i32, i32, i64, vp, c.POINTER(i64)]
+    lib.pnn_debug_get_activation.restype = i32
     lib.pnn_version.argtypes = []
     lib.pnn_version.restype = c.c_char_p
     _lib = lib

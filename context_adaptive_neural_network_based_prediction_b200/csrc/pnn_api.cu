@@ -743,6 +743,34 @@ int pnn_set_precision(pnn_handle* h, int precision) {
     return 0;
 }
 
+int pnn_debug_get_activation(pnn_handle* h, int width, int is_fc, int buffer_index, int64_t n_samples, float* out,
+                             int64_t* elems_per_sample) {
+    if (!h) return -1;
+    try {
+        Net& net = *find_net(h, width, is_fc);
+        if (buffer_index < 0 || buffer_index >= (int)net.buf_elems.size()) throw std::runtime_error("no such activation buffer");
+        const int64_t per = net.buf_elems[buffer_index];
+        if (elems_per_sample) *elems_per_sample = per;
+        if (!out) return 0;
+        if (n_samples > net.cap) throw std::runtime_error("more samples requested than the workspace holds");
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        const size_t count = (size_t)n_samples * per;
+        const bool split = h->precision == PNN_PRECISION_BF16X3 && !net.buf_fp32_only[buffer_index];
+        if (!split) {
+            CUDA_TRY(cudaMemcpy(out, net.ws0[buffer_index]->p, count * 4, cudaMemcpyDeviceToHost));
+        } else {
+            std::vector<uint16_t> hi(count), lo(count);
+            CUDA_TRY(cudaMemcpy(hi.data(), net.ws0[buffer_index]->p, count * 2, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(lo.data(), net.ws1[buffer_index]->p, count * 2, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < count; ++i) out[i] = bf16_to_float(hi[i]) + bf16_to_float(lo[i]);
+        }
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
 int64_t pnn_launch_count(pnn_handle* h) { return h ? h->launches : 0; }
 
 float pnn_last_hm_device_ms(pnn_handle* h) { return h ? h->hm_ms : 0.f; }

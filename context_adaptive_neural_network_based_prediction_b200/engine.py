@@ -65,6 +65,16 @@ class Engine(object):
     def last_hm_device_ms(self):
         return float(self._lib.pnn_last_hm_device_ms(self._h))
 
+    def get_activation(self, width_target, is_fully_connected, buffer_index, n_samples):
+        """Inspection hook: activation buffer `buffer_index` as left by the last call, float32 [n, elems]."""
+        per = ctypes.c_int64()
+        self._check(self._lib.pnn_debug_get_activation(self._h, width_target, int(bool(is_fully_connected)), buffer_index,
+                                                       0, None, ctypes.byref(per)))
+        out = numpy.empty((n_samples, per.value), dtype=numpy.float32)
+        self._check(self._lib.pnn_debug_get_activation(self._h, width_target, int(bool(is_fully_connected)), buffer_index,
+                                                       n_samples, _ptr(out), ctypes.byref(per)))
+        return out
+
     # ------------------------------------------------------------------ offline path, host buffers
     def predict_batch(self, width_target, is_fully_connected, above_or_flat, left=None):
         """pnn.batching.predict_by_batch_via_pnn equivalent: float32 contexts -> float32 [N, W, W, 1]."""

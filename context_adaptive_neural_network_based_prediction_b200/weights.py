@@ -120,8 +120,9 @@ def save_flat(path, width_target, is_fully_connected, weights):
         for n, off, nbytes in entries:
             f.seek(off)
             f.write(numpy.ascontiguousarray(weights[n], dtype='<f4').tobytes())
-        f.seek(offset - 1)
-        f.write(b'\0')
+        f.seek(0, 2)
+        if f.tell() < offset:
+            f.write(b'\0' * (offset - f.tell()))
 
 
 def load_flat(path):

@@ -131,6 +131,15 @@ int64_t pnn_launch_count(pnn_handle* h);
 /* Device time (ms, CUDA events on the handle's stream) of the last pnn_predict_hm call. */
 float pnn_last_hm_device_ms(pnn_handle* h);
 
+/*
+ * Inspection hook (tracing aid, no reference counterpart): copies activation buffer `buffer_index` of the
+ * given net, as left by the LAST call, to the host as float32 [n_samples, elements per sample].
+ * Buffer 0.. follow the layer order; returns the elements per sample in *elems_per_sample
+ * (out may be NULL to query it).
+ */
+int pnn_debug_get_activation(pnn_handle* h, int width, int is_fully_connected, int buffer_index, int64_t n_samples,
+                             float* out, int64_t* elems_per_sample);
+
 /* Library version string. */
 const char* pnn_version(void);
 

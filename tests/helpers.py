@@ -7,6 +7,10 @@ from context_adaptive_neural_network_based_prediction_b200 import weights as W
 
 MEAN = 117.8952234192841
 
+# weight gains that bring the outputs of the randomly initialised nets to tens of pixel units (the trained
+# nets' range); the reference initialisers alone give |output| < 1 for the deep convolutional nets
+GAIN = {(4, True): 1.6, (8, True): 1.6, (4, False): 2.6, (8, False): 2.0, (16, False): 1.9, (32, False): 2.0, (64, False): 2.05}
+
 
 def synthetic_image(height, width, seed):
     """clip(128 + 60 sin(x/17) + 40 cos(y/11) + N(0, 4^2))."""

@@ -65,13 +65,16 @@ def test_param_counts_and_flat_roundtrip(tmp_path):
     for (w, fc), count in expect.items():
         shapes = W.tensor_shapes(w, fc)
         assert sum(int(numpy.prod(s)) for s in shapes.values()) == count
-    wts = W.init_weights(8, False, 3, bias_std=0.1)
-    path = str(tmp_path / 'n.pnnw')
-    W.save_flat(path, 8, False, wts)
-    w, fc, back = W.load_flat(path)
-    assert (w, fc) == (8, False) and list(back) == list(wts)
-    for k in wts:
-        numpy.testing.assert_array_equal(back[k], wts[k])
+    # FC-8 ends with a 256-byte tensor (exactly one alignment unit): its last byte must survive the padding
+    for width, is_fc in ((8, False), (8, True), (4, True)):
+        wts = W.init_weights(width, is_fc, 3, bias_std=0.1)
+        path = str(tmp_path / ('n_%d_%d.pnnw' % (width, is_fc)))
+        W.save_flat(path, width, is_fc, wts)
+        assert os.path.getsize(path) % 256 == 0
+        w, fc, back = W.load_flat(path)
+        assert (w, fc) == (width, is_fc) and list(back) == list(wts)
+        for k in wts:
+            numpy.testing.assert_array_equal(back[k], wts[k])
 
 
 def test_initialisers_follow_reference():

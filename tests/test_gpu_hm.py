@@ -27,7 +27,7 @@ def _oracle_hm(wts, width, plane, orow, ocol, flags, n_avail):
 def test_hm_call_pair(engine, weights_dir, width):
     """Net selection by width as TComPrediction.cpp:564; availability patterns as TComPattern.cpp:260-280."""
     is_fc = width <= 8
-    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=40 + width, gain=1.6 if is_fc else 1.25)
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=40 + width, gain=helpers.GAIN[(width, is_fc)])
     engine.load_net(path)
     engine.set_precision('bf16x3')
     plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 5).astype(numpy.int32)

@@ -41,8 +41,7 @@ def _blocks(images, width, limit=None, seed=0):
                                               (64, False, 6), (4, False, 800), (8, False, 500)])
 def test_image_blocks_parity(engine, weights_dir, width, is_fc, limit, precision):
     """Fused gather + net + epilogue + PSNR against the oracle; gain > 1 so that outputs span tens of pixel units."""
-    gain = 1.6 if is_fc else 1.25
-    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=width + 100 * int(is_fc), gain=gain)
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=width + 100 * int(is_fc), gain=helpers.GAIN[(width, is_fc)])
     engine.load_net(path)
     engine.set_precision(precision)
     images = _image_set(2, max(96, 3 * width), max(128, 4 * width))
@@ -76,7 +75,7 @@ def test_real_checkpoints_against_golden(engine, golden_dir, width):
 @pytest.mark.parametrize('width,is_fc', [(8, True), (16, False)])
 def test_masks_and_image_borders(engine, weights_dir, width, is_fc):
     """Masks in {0, 4, ..., W} (sets/common.py:444-461); context parts outside the image are masked like unavailable units."""
-    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=7, gain=1.5)
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=7, gain=helpers.GAIN[(width, is_fc)])
     engine.load_net(path)
     engine.set_precision('bf16x3')
     images = _image_set(1, 5 * width, 6 * width)
@@ -97,7 +96,7 @@ def test_masks_and_image_borders(engine, weights_dir, width, is_fc):
 @pytest.mark.parametrize('width,is_fc', [(4, True), (8, True), (16, False)])
 def test_predict_batch_matches_fused_gather(engine, weights_dir, width, is_fc):
     """pnn_predict_batch on pre-processed contexts == pnn_predict_image_blocks, bit for bit (same kernels, same order)."""
-    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=11, gain=1.4)
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=11, gain=helpers.GAIN[(width, is_fc)])
     engine.load_net(path)
     engine.set_precision('bf16x3')
     images = _image_set(1, 96, 128)
@@ -125,7 +124,7 @@ def test_empty_and_single_inputs(engine, weights_dir):
 @pytest.mark.parametrize('width,is_fc', [(8, True), (16, False)])
 def test_rebatching_and_repeat_are_bit_identical(engine, weights_dir, width, is_fc):
     """Fixed reduction order: a block's prediction does not depend on the batch it is computed in."""
-    path, _ = helpers.make_net_file(weights_dir, width, is_fc, seed=21, gain=1.5)
+    path, _ = helpers.make_net_file(weights_dir, width, is_fc, seed=21, gain=helpers.GAIN[(width, is_fc)])
     engine.load_net(path)
     engine.set_precision('bf16x3')
     images = _image_set(3, 96, 160)
