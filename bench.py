@@ -1,0 +1,406 @@
+"""Benchmark of the PNN hot path (BASELINE.json configs[1]).
+
+Workload (per GPU; "scaling": "weak"): 100 synthetic BSDS-shaped 320x480 luminance images, every
+W-aligned block with an in-image context anchor, for W in {4, 8, 16, 32} (nets FC-4, FC-8, CONV-16,
+CONV-32, seeded random init -- the pretrained HM weights are not shipped with the reference), outputs =
+rounded uint8 predictions, per-block PSNR (float64) and win flag against a supplied baseline PSNR array;
+ONE gather of the statistics to rank 0.  A "step" is one pass over all four block sizes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`value`  : predictions/s with images and block lists resident in HBM (device-pointer C-ABI calls).
+`e2e`    : the same metric through the host-pointer C-ABI call (pinned host buffers; H2D of the images
+           and block lists and D2H of predictions + PSNRs inside the timed region).
+`--impl reference`: the CPU stand-in of the reference path (fp32 oracle on torch-CPU, all host threads, the
+           reference's batch size of 10) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WIDTHS = ((4, True), (8, True), (16, False), (32, False))
+N_IMAGES, HEIGHT, WIDTH_IMAGE = 100, 320, 480
+MEAN = 117.8952234192841
+METRIC = 'PNN predictions/sec (4x4+8x8+16x16+32x32 blocks, 100 BSDS-shaped images per GPU)'
+# algorithmic FLOPs per prediction = 2 * MACs (dense count)
+MACS = {4: 2995200, 8: 3340800, 16: 48750592, 32: 273317888}
+
+
+def synthetic_image(height, width, seed):
+    """clip(128 + 60 sin(x/17) + 40 cos(y/11) + N(0, 4^2)), default_rng(seed)."""
+    rng = numpy.random.default_rng(seed)
+    y, x = numpy.mgrid[0:height, 0:width]
+    img = 128. + 60. * numpy.sin(x / 17.) + 40. * numpy.cos(y / 11.) + rng.normal(0., 4., (height, width))
+    return numpy.clip(numpy.round(img), 0, 255).astype(numpy.uint8)
+
+
+def workload_config(n_gpus):
+    from context_adaptive_neural_network_based_prediction_b200 import offline
+    blocks = {w: len(offline.grid_blocks(HEIGHT, WIDTH_IMAGE, w)[0]) * N_IMAGES for w, _ in WIDTHS}
+    return {
+        'workload': 'configs[1]: PNN 4x4/8x8/16x16/32x32 batched prediction over 100 synthetic BSDS-shaped '
+                    '(320x480 after the reference 1-px crop) images per GPU, PSNR / win statistics gathered',
+        'images_per_gpu': N_IMAGES, 'image_shape': [HEIGHT, WIDTH_IMAGE],
+        'nets': ['FC-4', 'FC-8', 'CONV-16', 'CONV-32'], 'weights': 'seeded random init (reference initialisers)',
+        'blocks_per_gpu': {str(w): n for w, n in blocks.items()}, 'masks': [0, 0],
+        'parallelism': 'images sharded over %d GPU(s), no data-path collective, one NCCL gather of statistics' % n_gpus,
+        'l2': 'explicit flush (256 MiB write) before every timed step; per-step activations (>10 GB) exceed the 126 MB L2 anyway',
+    }, blocks
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index),
+                 '--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+                 'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, sm_max, reasons = [], None, set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for t, line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 7 or not (t0 - 0.1 <= t <= t1 + 0.3):
+                continue
+            try:
+                sm.append(float(parts[0]))
+                sm_max = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(numpy.median(sm)) if sm else None, 'sm_max_mhz': sm_max, 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def make_weights(directory):
+    from context_adaptive_neural_network_based_prediction_b200 import weights
+    paths, tensors = {}, {}
+    for w, is_fc in WIDTHS:
+        wts = weights.init_weights(w, is_fc, seed=w)          # rng(W), reference initialisers
+        path = os.path.join(directory, 'net_%d.pnnw' % w)
+        weights.save_flat(path, w, is_fc, wts)
+        paths[w], tensors[w] = path, wts
+    return paths, tensors
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU stand-in of the reference path (bounded sample)
+# ----------------------------------------------------------------------------------------------
+
+def cpu_reference_rates(tensors, seconds_per_size, batch_size=10):
+    """fp32 oracle on torch-CPU with every host thread, driven like pnn/batching.py:74-87 (sess.run per batch of 10).
+
+    Only the network forward is timed (contexts pre-gathered): generous to the CPU.
+    """
+    import torch
+    from oracle import context, nets
+    torch.set_num_threads(os.cpu_count() or 1)
+    images = numpy.stack([synthetic_image(HEIGHT, WIDTH_IMAGE, s) for s in range(2)])
+    from context_adaptive_neural_network_based_prediction_b200 import offline
+    rates, counts = {}, {}
+    for w, is_fc in WIDTHS:
+        rows, cols = offline.grid_blocks(HEIGHT, WIDTH_IMAGE, w)
+        n = min(len(rows), 400)
+        above, left, flat, _ = context.gather_image_blocks(images, numpy.zeros(n, int), rows[:n], cols[:n], w, MEAN, 0, 0)
+        nets.forward(tensors[w], w, is_fc, (flat[:batch_size],) if is_fc else (above[:batch_size], left[:batch_size]))
+        done, t0 = 0, time.perf_counter()
+        while True:
+            i = (done // batch_size * batch_size) % (n - batch_size + 1)
+            if is_fc:
+                nets.forward_fc(tensors[w], flat[i:i + batch_size])
+            else:
+                nets.forward_conv(tensors[w], above[i:i + batch_size], left[i:i + batch_size])
+            done += batch_size
+            if time.perf_counter() - t0 >= seconds_per_size and done >= 3 * batch_size:
+                break
+        rates[w] = done / (time.perf_counter() - t0)
+        counts[w] = done
+    return rates, counts
+
+
+def aggregate_rate(rates, blocks):
+    total = float(sum(blocks.values()))
+    return total / sum(blocks[w] / rates[w] for w in blocks)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cfg, blocks = workload_config(args.gpus)
+    tmp = tempfile.mkdtemp(prefix='pnn_bench_')
+    _, tensors = make_weights(tmp)
+    cpu_reference_rates(tensors, 0.5)                         # warm-up
+    values, counts = [], {}
+    t_all = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        rates, counts = cpu_reference_rates(tensors, args.reference_seconds)
+        values.append(aggregate_rate(rates, blocks))
+    value = float(numpy.mean(values))
+    cores = os.cpu_count() or 1
+    sample = ('network forward only, batches of 10 (pnn/batching.py), %s blocks per size per step, rate extrapolated to the '
+              'full block mix' % {str(k): v for k, v in counts.items()})
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'predictions/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(blocks.values()) / value,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': cfg,
+        'cpu_baseline': {'value': value, 'unit': 'predictions/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                         'note': 'TensorFlow 1.x is not installable offline; the fp32 oracle on torch-CPU (oneDNN/MKL) stands in '
+                                 'for the reference TF-CPU path'},
+        'e2e': {'value': value, 'unit': 'predictions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'wall_s': time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--reference-seconds', type=float, default=3.0, help='CPU seconds per block size per step')
+    ap.add_argument('--cpu-baseline-seconds', type=float, default=4.0)
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--report', action='store_true', help='print the per-kernel table to stderr')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from context_adaptive_neural_network_based_prediction_b200 import Engine, offline
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    args.warmup = max(args.warmup, 3)
+    cfg, blocks = workload_config(world)
+    tmp = tempfile.mkdtemp(prefix='pnn_bench_')
+    paths, tensors = make_weights(tmp)
+    eng = Engine(mean_training=MEAN, device=local_rank)
+    for w, _ in WIDTHS:
+        eng.load_net(paths[w])
+    eng.set_precision(args.precision)
+
+    # this rank's image shard: images rank*100 .. rank*100+99 of the (weak-scaling) image set
+    images_np = numpy.stack([synthetic_image(HEIGHT, WIDTH_IMAGE, rank * N_IMAGES + i) for i in range(N_IMAGES)])
+    images_pin = torch.from_numpy(images_np).pin_memory()
+    d_images = images_pin.to(dev)
+    total = sum(blocks.values())
+    d_psnr = torch.empty(total, dtype=torch.float64, device=dev)
+    d_win = torch.empty(total, dtype=torch.uint8, device=dev)
+    d_base = torch.full((total,), 30., dtype=torch.float64, device=dev)     # supplied baseline PSNRs (synthetic: 30 dB)
+    per_w, off = {}, 0
+    for w, is_fc in WIDTHS:
+        idx, rows, cols = offline.blocks_of_images(N_IMAGES, HEIGHT, WIDTH_IMAGE, w)
+        n = len(rows)
+        per_w[w] = {
+            'is_fc': is_fc, 'n': n, 'off': off,
+            'h_idx': torch.from_numpy(idx).pin_memory(), 'h_rows': torch.from_numpy(rows).pin_memory(),
+            'h_cols': torch.from_numpy(cols).pin_memory(),
+            'd_u8': torch.empty((n, w * w), dtype=torch.uint8, device=dev),
+            'h_u8': torch.empty((n, w, w), dtype=torch.uint8).pin_memory(),
+            'h_psnr': torch.empty(n, dtype=torch.float64).pin_memory(),
+        }
+        for k in ('idx', 'rows', 'cols'):
+            per_w[w]['d_' + k] = per_w[w]['h_' + k].to(dev)
+        off += n
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    size_events = {w: [] for w, _ in WIDTHS}
+
+    def step_device(record=False):
+        stream = torch.cuda.current_stream().cuda_stream
+        for w, _ in WIDTHS:
+            p = per_w[w]
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            eng.predict_image_blocks_device(w, p['is_fc'], d_images.data_ptr(), N_IMAGES, HEIGHT, WIDTH_IMAGE,
+                                            p['d_idx'].data_ptr(), p['d_rows'].data_ptr(), p['d_cols'].data_ptr(), p['n'],
+                                            (0, 0), None, p['d_u8'].data_ptr(), d_psnr.data_ptr() + 8 * p['off'], stream)
+            if record:
+                e1.record()
+                size_events[w].append((e0, e1))
+        eng.win_flags_device(d_psnr.data_ptr(), d_base.data_ptr(), total, d_win.data_ptr(), stream)
+        return offline.gather_statistics(d_psnr, d_win, rank, world)
+
+    def step_e2e():
+        psnrs = []
+        for w, _ in WIDTHS:
+            p = per_w[w]
+            eng.predict_image_blocks(w, p['is_fc'], images_pin.numpy(), p['h_rows'].numpy(), p['h_cols'].numpy(),
+                                     p['h_idx'].numpy(), want_float=False, out_uint8=p['h_u8'].numpy(),
+                                     out_psnr=p['h_psnr'].numpy())
+            psnrs.append(p['h_psnr'])
+        psnr_all = torch.cat(psnrs)
+        wins = (psnr_all - 30. > 0.).to(torch.uint8)
+        if world > 1:
+            g_psnr, g_win = offline.gather_statistics(psnr_all.to(dev), wins.to(dev), rank, world)
+            if rank == 0:
+                return offline.reduce_statistics(g_psnr.cpu().numpy(), g_win.cpu().numpy())
+            return None
+        return offline.reduce_statistics(psnr_all.numpy(), wins.numpy())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, record_sizes=False):
+        """K steps, each preceded by an L2 flush, timed with CUDA events on the launching stream."""
+        events = []
+        barrier()
+        t0 = time.time()
+        for _ in range(steps):
+            flush_buf.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(True) if record_sizes else fn()
+            e1.record()
+            events.append((e0, e1))
+        barrier()
+        t1 = time.time()
+        ms = sum(a.elapsed_time(b) for a, b in events)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, t1
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count
+    eng.set_profiling(True)
+    eng.profile_report()
+    ms_total, t0, t1 = timed(step_device, args.steps, record_sizes=True)
+    prof = eng.profile_report()
+    eng.set_profiling(False)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_per_step = ms_total / args.steps
+    value = world * total / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm (host buffers through the C ABI) -----------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    walls = []
+    for _ in range(args.steps):
+        barrier()
+        tw = time.perf_counter()
+        stats = step_e2e()
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - tw)
+    e2e_s = float(numpy.mean(walls))
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = sum(images_np.nbytes + 12 * per_w[w]['n'] for w, _ in WIDTHS)
+    d2h = sum(per_w[w]['n'] * (w * w + 8) for w, _ in WIDTHS)
+
+    if rank == 0:
+        per_size = {}
+        for w, _ in WIDTHS:
+            ms_w = float(numpy.mean([a.elapsed_time(b) for a, b in size_events[w]]))
+            per_size[str(w)] = {'predictions_per_s_per_gpu': per_w[w]['n'] / (ms_w * 1e-3), 'ms': ms_w,
+                                'tflops_algorithmic': 2. * MACS[w] * per_w[w]['n'] / (ms_w * 1e-3) / 1e12}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = peaks.get('bf16_tflops_sustained', 1590.0 if not peaks else None) or 1590.0
+        achieved = prof['gemm_flops'] / (prof['gemm_ms'] * 1e-3) / 1e12 if prof['gemm_ms'] > 0 else 0.
+        roofline = {
+            'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 bf16x3 implicit GEMM)', 'achieved': achieved, 'peak': peak,
+            'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks
+                           else 'fallback 1.59 PFLOP/s (B200_PROFILING.md)',
+            'mma_passes': 3, 'frac_of_tensor_issue': 3. * achieved / peak,
+            'gemm_launches_per_step': prof['gemm_launches'] / args.steps,
+            'gemm_ms_per_step': prof['gemm_ms'] / args.steps, 'other_kernels_ms_per_step': prof['other_ms'] / args.steps,
+            'note': 'achieved = algorithmic FLOPs (2*M*N*K of every GEMM-shaped layer launch) / summed CUDA-event time of those '
+                    'launches in the timed region; each algorithmic MAC costs 3 bf16 MMA passes (hi*hi + hi*lo + lo*hi)',
+        }
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'predictions/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16x3 (bf16 hi/lo operands, 3 MMA passes, f32 accumulate)'
+            if args.precision == 'bf16x3' else 'f32', 'data': 'synthetic', 'config': cfg,
+            'per_size': per_size, 'roofline': roofline,
+            'e2e': {'value': world * total / e2e_s, 'unit': 'predictions/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3 * e2e_s,
+                    'mean_psnr_pnn': stats['mean_psnr_pnn'], 'frequency_win_pnn': stats['frequency_win_pnn']},
+            'gpu_launches': launches, 'clocks': clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            t_cpu = time.perf_counter()
+            rates, counts = cpu_reference_rates(tensors, args.cpu_baseline_seconds)
+            line['cpu_baseline'] = {
+                'value': aggregate_rate(rates, blocks), 'unit': 'predictions/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+                'sample': 'network forward only (contexts pre-gathered), batches of 10 as pnn/batching.py drives sess.run, '
+                          '%s blocks per size, extrapolated to the full block mix' % {str(k): v for k, v in counts.items()},
+                'per_size': {str(w): rates[w] for w in rates}, 'seconds': time.perf_counter() - t_cpu,
+                'note': 'fp32 oracle on torch-CPU (oneDNN/MKL) standing in for the reference TF-CPU path (TensorFlow not installable)',
+            }
+        if args.report:
+            sys.stderr.write(prof['text'] + '\n')
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == '__main__':
+    main()

@@ -14,7 +14,8 @@ EXPORTS = (
     'pnn_create', 'pnn_destroy', 'pnn_last_error', 'pnn_load_net', 'pnn_set_precision',
     'pnn_set_context', 'pnn_predict_hm', 'pnn_predict_batch', 'pnn_predict_image_blocks',
     'pnn_predict_batch_device', 'pnn_predict_image_blocks_device', 'pnn_launch_count',
-    'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation',
+    'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation', 'pnn_win_flags_device', 'pnn_set_profiling',
+    'pnn_profile_report',
 )
 
 PRECISION_FP32 = 0
@@ -63,6 +64,12 @@ def load():
     lib.pnn_last_hm_device_ms.restype = c.c_float
     lib.pnn_debug_get_activation.argtypes = [vp, i32, i32, i32, i64, vp, c.POINTER(i64)]
     lib.pnn_debug_get_activation.restype = i32
+    lib.pnn_win_flags_device.argtypes = [vp, vp, vp, i64, vp, vp]
+    lib.pnn_win_flags_device.restype = i32
+    lib.pnn_set_profiling.argtypes = [vp, i32]
+    lib.pnn_set_profiling.restype = i32
+    lib.pnn_profile_report.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(c.c_double), c.POINTER(i64), c.POINTER(c.c_double)]
+    lib.pnn_profile_report.restype = c.c_char_p
     lib.pnn_version.argtypes = []
     lib.pnn_version.restype = c.c_char_p
     _lib = lib

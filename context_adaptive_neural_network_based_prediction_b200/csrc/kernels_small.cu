@@ -293,4 +293,18 @@ int launch_psnr(const uint8_t* images, const int32_t* image_index, const int32_t
     return 1;
 }
 
+// reference comparing_pnn_ipfcns_hevc_best_mode.py:87: numpy.count_nonzero(psnrs_nn - psnrs_hevc_best_mode > 0.)
+__global__ void win_flags_kernel(const double* __restrict__ psnr, const double* __restrict__ base, int64_t n,
+                                 uint8_t* __restrict__ win) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        win[i] = (psnr[i] - base[i] > 0.) ? 1 : 0;
+    }
+}
+
+int launch_win_flags(const double* psnr, const double* baseline, int64_t n, uint8_t* win, cudaStream_t stream) {
+    if (n == 0) return 0;
+    win_flags_kernel<<<grid_for(n, 256), 256, 0, stream>>>(psnr, baseline, n, win);
+    return 1;
+}
+
 }  // namespace pnn

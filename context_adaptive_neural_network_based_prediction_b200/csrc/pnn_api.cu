@@ -416,9 +416,51 @@ struct pnn_handle {
     int hm_unit_w = 4, hm_left_rows = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float hm_ms = 0.f;
+    // per-kernel profiling
+    struct ProfRec {
+        std::string name;
+        int64_t M, N, K;
+        double flops;
+        bool is_gemm;
+        cudaEvent_t e0, e1;
+    };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+    std::string prof_text;
 };
 
 namespace {
+
+cudaEvent_t take_event(pnn_handle* h) {
+    if (!h->event_pool.empty()) {
+        cudaEvent_t e = h->event_pool.back();
+        h->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    return e;
+}
+
+// RAII bracket of one launch when profiling is on
+struct ProfScope {
+    pnn_handle* h;
+    cudaStream_t s;
+    size_t idx = 0;
+    bool on;
+    ProfScope(pnn_handle* h_, cudaStream_t s_, const char* name, int64_t M, int64_t N, int64_t K, bool is_gemm)
+        : h(h_), s(s_), on(h_->profiling) {
+        if (!on) return;
+        pnn_handle::ProfRec r{name, M, N, K, 2.0 * (double)M * (double)N * (double)K, is_gemm, take_event(h), take_event(h)};
+        cudaEventRecord(r.e0, s);
+        h->prof.push_back(r);
+        idx = h->prof.size() - 1;
+    }
+    ~ProfScope() {
+        if (on) cudaEventRecord(h->prof[idx].e1, s);
+    }
+};
 
 Net* find_net(pnn_handle* h, int width, int is_fc) {
     auto it = h->nets.find({width, is_fc ? 1 : 0});
@@ -486,6 +528,7 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.w_fp32 = st.d_w32;
                 L.w_tiles = st.d_wt;
                 L.bias = st.d_bias;
+                ProfScope ps(h, stream, split ? "gemm_tc" : "gemm_fp32", L.M, st.g.N, st.g.K, true);
                 h->launches += split ? launch_gemm_tc(L, stream) : launch_gemm_fp32(L, stream);
                 break;
             }
@@ -497,6 +540,7 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.bias = st.d_bias;
                 L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.OH = st.OH; L.OW = st.OW; L.Cout = st.C;
                 L.k = st.k; L.stride = st.stride; L.pad = st.pad; L.split = split;
+                ProfScope ps(h, stream, "conv0", n * st.OH * st.OW, st.C, st.k * st.k, false);
                 h->launches += launch_conv0(L, stream);
                 break;
             }
@@ -508,6 +552,7 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.w = st.d_w32;
                 L.bias = st.d_bias;
                 L.n = (int)n; L.C = st.C; L.split = split;
+                ProfScope ps(h, stream, "merger", n * st.C, 16, 80, false);
                 h->launches += launch_merger(L, stream);
                 break;
             }
@@ -519,6 +564,8 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.fin = fin;
                 L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.Cin = st.C; L.k = st.k; L.stride = st.stride; L.pad = st.pad;
                 L.split = split;
+                ProfScope ps(h, stream, "tconv_last", n * st.IH * st.stride * st.IW * st.stride, 1,
+                             (int64_t)st.C * ((st.k + st.stride - 1) / st.stride) * ((st.k + st.stride - 1) / st.stride), false);
                 h->launches += launch_tconv_last(L, stream);
                 break;
             }
@@ -571,7 +618,10 @@ void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int H
             G.pitch_left = 2 * px;
             G.split = 0;
         }
-        h->launches += launch_gather_image(G, stream);
+        {
+            ProfScope ps(h, stream, "gather_image", m * 5 * px, 1, 1, false);
+            h->launches += launch_gather_image(G, stream);
+        }
         FinalOut fin{};
         fin.raw = d_f32 ? d_f32 + s0 * px : nullptr;
         uint8_t* u8 = d_u8 ? d_u8 + s0 * px : (d_psnr ? (uint8_t*)net.out_u8.p : nullptr);
@@ -580,6 +630,7 @@ void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int H
         fin.round_mode = PNN_ROUND_HALF_EVEN;
         run_net(h, net, m, fin, stream);
         if (d_psnr) {
+            ProfScope ps(h, stream, "psnr", m * px, 1, 1, false);
             h->launches += launch_psnr(d_images, G.image_index, G.rows, G.cols, m, H, Wimg, W, u8, d_psnr + s0, stream);
         }
     }
@@ -769,6 +820,68 @@ int pnn_debug_get_activation(pnn_handle* h, int width, int is_fc, int buffer_ind
         return fail(h, e);
     }
     return 0;
+}
+
+int pnn_win_flags_device(pnn_handle* h, const double* d_psnr, const double* d_base, int64_t n, uint8_t* d_win, void* stream) {
+    if (!h) return -1;
+    try {
+        if (n < 0 || !d_psnr || !d_base || !d_win) throw std::runtime_error("bad arguments");
+        CUDA_TRY(cudaSetDevice(h->device));
+        h->launches += launch_win_flags(d_psnr, d_base, n, d_win, (cudaStream_t)stream);
+        CUDA_TRY(cudaGetLastError());
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_set_profiling(pnn_handle* h, int enabled) {
+    if (!h) return -1;
+    h->profiling = enabled != 0;
+    return 0;
+}
+
+const char* pnn_profile_report(pnn_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, double* other_ms) {
+    if (!h) return "";
+    double g_ms = 0., g_fl = 0., o_ms = 0.;
+    int64_t g_n = 0;
+    try {
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        struct Agg { int64_t launches = 0; double ms = 0., flops = 0.; };
+        std::map<std::string, Agg> agg;
+        for (auto& r : h->prof) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
+            h->event_pool.push_back(r.e0);
+            h->event_pool.push_back(r.e1);
+            char key[160];
+            snprintf(key, sizeof(key), "%-12s %10lld %5lld %6lld", r.name.c_str(), (long long)r.M, (long long)r.N, (long long)r.K);
+            Agg& a = agg[key];
+            a.launches += 1;
+            a.ms += ms;
+            a.flops += r.flops;
+            if (r.is_gemm) { g_ms += ms; g_fl += r.flops; g_n += 1; } else { o_ms += ms; }
+        }
+        h->prof.clear();
+        std::ostringstream os;
+        os << "kernel                M     N      K  launches        ms   TFLOP/s\n";
+        for (auto& kv : agg) {
+            char line[256];
+            snprintf(line, sizeof(line), "%s %9lld %9.3f %9.2f\n", kv.first.c_str(), (long long)kv.second.launches, kv.second.ms,
+                     kv.second.ms > 0 ? kv.second.flops / (kv.second.ms * 1e-3) / 1e12 : 0.);
+            os << line;
+        }
+        h->prof_text = os.str();
+    } catch (const std::exception& e) {
+        h->error = e.what();
+        h->prof_text = std::string("error: ") + e.what();
+    }
+    if (gemm_ms) *gemm_ms = g_ms;
+    if (gemm_flops) *gemm_flops = g_fl;
+    if (gemm_launches) *gemm_launches = g_n;
+    if (other_ms) *other_ms = o_ms;
+    return h->prof_text.c_str();
 }
 
 int64_t pnn_launch_count(pnn_handle* h) { return h ? h->launches : 0; }

@@ -156,6 +156,8 @@ struct GatherHmLaunch {
 };
 int launch_gather_hm(const GatherHmLaunch& L, cudaStream_t stream);
 
+int launch_win_flags(const double* psnr, const double* baseline, int64_t n, uint8_t* win, cudaStream_t stream);
+
 // fp32 -> (fp32 copy | split planes)
 int launch_convert_input(const float* src, Act dst, int64_t n_elems, int split, cudaStream_t stream);
 

@@ -65,6 +65,21 @@ class Engine(object):
     def last_hm_device_ms(self):
         return float(self._lib.pnn_last_hm_device_ms(self._h))
 
+    def set_profiling(self, enabled):
+        self._check(self._lib.pnn_set_profiling(self._h, int(bool(enabled))))
+
+    def profile_report(self):
+        """-> dict(text, gemm_ms, gemm_flops, gemm_launches, other_ms); resets the counters."""
+        g_ms, g_fl, o_ms = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        g_n = ctypes.c_int64()
+        text = self._lib.pnn_profile_report(self._h, ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n),
+                                            ctypes.byref(o_ms)).decode()
+        return {'text': text, 'gemm_ms': g_ms.value, 'gemm_flops': g_fl.value, 'gemm_launches': g_n.value,
+                'other_ms': o_ms.value}
+
+    def win_flags_device(self, d_psnr, d_baseline, n, d_win, stream=0):
+        self._check(self._lib.pnn_win_flags_device(self._h, d_psnr, d_baseline, n, d_win, stream))
+
     def get_activation(self, width_target, is_fully_connected, buffer_index, n_samples):
         """Inspection hook: activation buffer `buffer_index` as left by the last call, float32 [n, elems]."""
         per = ctypes.c_int64()
@@ -95,7 +110,8 @@ class Engine(object):
         return out
 
     def predict_image_blocks(self, width_target, is_fully_connected, images_uint8, rows, cols, image_index=None,
-                             masks=(0, 0), want_float=True, want_uint8=True, want_psnr=True):
+                             masks=(0, 0), want_float=True, want_uint8=True, want_psnr=True,
+                             out_float=None, out_uint8=None, out_psnr=None):
         """Fused gather + net + epilogue for blocks of uint8 images [n_images, H, W_img] (or [H, W_img]).
 
         Returns a dict with 'predictions_float32' [N, W, W] (raw), 'predictions_uint8' [N, W, W] and
@@ -109,18 +125,22 @@ class Engine(object):
         n = rows.shape[0]
         idx = None if image_index is None else numpy.ascontiguousarray(image_index, dtype=numpy.int32)
         w = width_target
-        f32 = numpy.empty((n, w, w), dtype=numpy.float32) if want_float else None
-        u8 = numpy.empty((n, w, w), dtype=numpy.uint8) if want_uint8 else None
-        psnr = numpy.empty((n,), dtype=numpy.float64) if want_psnr else None
+        # caller-provided (e.g. pinned) output arrays are used as they are
+        f32 = out_float if out_float is not None else (numpy.empty((n, w, w), dtype=numpy.float32) if want_float else None)
+        u8 = out_uint8 if out_uint8 is not None else (numpy.empty((n, w, w), dtype=numpy.uint8) if want_uint8 else None)
+        psnr = out_psnr if out_psnr is not None else (numpy.empty((n,), dtype=numpy.float64) if want_psnr else None)
+        for arr, dt, count in ((f32, numpy.float32, n * w * w), (u8, numpy.uint8, n * w * w), (psnr, numpy.float64, n)):
+            if arr is not None and (arr.dtype != dt or arr.size != count or not arr.flags['C_CONTIGUOUS']):
+                raise ValueError('an output array has the wrong dtype, size or layout')
         self._check(self._lib.pnn_predict_image_blocks(
             self._h, w, int(bool(is_fully_connected)), _ptr(img), img.shape[0], img.shape[1], img.shape[2],
             _ptr(idx), _ptr(rows), _ptr(cols), n, int(masks[0]), int(masks[1]), _ptr(f32), _ptr(u8), _ptr(psnr)))
         out = {}
-        if want_float:
+        if f32 is not None:
             out['predictions_float32'] = f32
-        if want_uint8:
+        if u8 is not None:
             out['predictions_uint8'] = u8
-        if want_psnr:
+        if psnr is not None:
             out['psnrs'] = psnr
         return out
 

@@ -1,0 +1,65 @@
+"""Offline batched evaluation sharded by image.
+
+Host-side mirror of the PNN half of the reference's `predict_mask`
+(comparing_pnn_ipfcns_hevc_best_mode.py:162-322): for every image of the rank's shard, every block
+is predicted, its PSNR and win flag against a supplied baseline are computed, and ONE gather brings the
+per-block statistics to rank 0, which reduces them to the reference's dictionary keys
+(`psnrs_pnn`, `mean_psnr_pnn`, `frequency_win_pnn`, comparing_pnn_...py:264-322).
+
+The blocks of different images are independent, so the shards need no data-path collective; the gather
+moves <= tens of MB and is latency-bound.
+"""
+import numpy
+
+
+def shard_image_indices(nb_images, rank, world_size):
+    """Round-robin assignment of images to ranks (image i goes to rank i % world_size)."""
+    return list(range(rank, nb_images, world_size))
+
+
+def grid_blocks(height, width_image, width_target):
+    """All W-aligned target blocks whose context anchor (row - W, col - W) lies inside the image."""
+    rows, cols = numpy.meshgrid(numpy.arange(width_target, height - width_target + 1, width_target),
+                                numpy.arange(width_target, width_image - width_target + 1, width_target), indexing='ij')
+    return rows.ravel().astype(numpy.int32), cols.ravel().astype(numpy.int32)
+
+
+def blocks_of_images(nb_images, height, width_image, width_target):
+    """(image_index, rows, cols) int32 arrays for all grid blocks of `nb_images` images, image-major."""
+    rows, cols = grid_blocks(height, width_image, width_target)
+    idx = numpy.repeat(numpy.arange(nb_images, dtype=numpy.int32), len(rows))
+    return idx, numpy.tile(rows, nb_images), numpy.tile(cols, nb_images)
+
+
+def gather_statistics(psnrs_local, wins_local, rank, world_size, group=None):
+    """ONE gather of the per-block statistics to rank 0.
+
+    `psnrs_local` float64 and `wins_local` uint8 are torch tensors (CUDA for NCCL, CPU for gloo) of the same
+    length on every rank.  They are packed into one float64 message (win flags are exactly representable),
+    so a single collective is issued.  Returns (psnrs [world, n], wins [world, n]) on rank 0, (None, None)
+    elsewhere.
+    """
+    import torch
+    import torch.distributed as dist
+    packed = torch.cat([psnrs_local.to(torch.float64), wins_local.to(torch.float64)])
+    if world_size == 1:
+        out = [packed]
+    else:
+        out = [torch.empty_like(packed) for _ in range(world_size)] if rank == 0 else None
+        dist.gather(packed, out, dst=0, group=group)
+    if rank != 0:
+        return None, None
+    n = psnrs_local.numel()
+    stacked = torch.stack(out)
+    return stacked[:, :n], stacked[:, n:].to(torch.uint8)
+
+
+def reduce_statistics(psnrs, wins):
+    """The reference's result keys (comparing_pnn_ipfcns_hevc_best_mode.py:264-322) from the gathered arrays."""
+    psnrs = numpy.asarray(psnrs, dtype=numpy.float64).ravel()
+    wins = numpy.asarray(wins).ravel()
+    return {
+        'psnrs_pnn': psnrs,
+        'mean_psnr_pnn': float(psnrs.mean()) if psnrs.size else float('nan'),
+        'frequency_win_pnn': float(numpy.count_nonzero(wins)) / max(1, wins.size),
+    }

@@ -132,6 +132,24 @@ int64_t pnn_launch_count(pnn_handle* h);
 float pnn_last_hm_device_ms(pnn_handle* h);
 
 /*
+ * Win flags of the offline evaluation (reference comparing_pnn_ipfcns_hevc_best_mode.py:87):
+ * d_win[i] = (d_psnr[i] - d_psnr_baseline[i] > 0).  DEVICE pointers, asynchronous on `cuda_stream`.
+ */
+int pnn_win_flags_device(pnn_handle* h, const double* d_psnr, const double* d_psnr_baseline, int64_t n,
+                         uint8_t* d_win, void* cuda_stream);
+
+/*
+ * Per-kernel device timing (CUDA events around every launch on the launching stream).  Off by default.
+ * pnn_profile_report synchronises, aggregates by (kernel, shape) and returns a text table
+ * "kernel M N K launches ms flops"; the totals of the tcgen05 / fp32 GEMM kernel are returned in
+ * *gemm_ms / *gemm_flops / *gemm_launches and those of all other kernels in *other_ms (each may be NULL).
+ * The report resets the counters.
+ */
+int pnn_set_profiling(pnn_handle* h, int enabled);
+const char* pnn_profile_report(pnn_handle* h, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches,
+                               double* other_ms);
+
+/*
  * Inspection hook (tracing aid, no reference counterpart): copies activation buffer `buffer_index` of the
  * given net, as left by the LAST call, to the host as float32 [n_samples, elements per sample].
  * Buffer 0.. follow the layer order; returns the elements per sample in *elems_per_sample
