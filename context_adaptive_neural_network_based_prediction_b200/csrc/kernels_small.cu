@@ -16,46 +16,42 @@ static inline int grid_for(int64_t n, int block) {
 // ---------------------------------------------------------------------------------------------
 template <bool SPLIT>
 __global__ void gather_image_kernel(GatherLaunch L) {
+    // blockDim = (64, 4): threadIdx.y picks the block (target patch), threadIdx.x strides over its 5*W*W pixels
     const int W = L.W;
-    const int na = 3 * W * W, nl = 2 * W * W, per = na + nl;
-    const int64_t total = L.n * per;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = idx / per;
-        const int e = (int)(idx - i * per);
+    const int na = 3 * W * W, per = 5 * W * W, w3 = 3 * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; i < L.n; i += (int64_t)gridDim.x * blockDim.y) {
         const int img = L.image_index ? L.image_index[i] : 0;
         const int r0 = L.rows[i], c0 = L.cols[i];
-        int r, c;
-        bool masked;
-        if (e < na) {
-            const int rr = e / (3 * W), cc = e - rr * 3 * W;
-            r = r0 - W + rr;
-            c = c0 - W + cc;
-            masked = cc >= 3 * W - L.mask_w;
-        } else {
-            const int e2 = e - na;
-            const int rr = e2 / W, cc = e2 - rr * W;
-            r = r0 + rr;
-            c = c0 - W + cc;
-            masked = rr >= 2 * W - L.mask_h;
-        }
-        float v = 0.f;
-        if (!masked && r >= 0 && r < L.H && c >= 0 && c < L.Wimg) {
-            v = (float)L.images[((int64_t)img * L.H + r) * L.Wimg + c] - L.mean;
-        }
-        if (e < na) {
-            act_store<SPLIT>(L.above, i * L.pitch_above + e, v);
-        } else {
-            act_store<SPLIT>(L.left, i * L.pitch_left + (e - na), v);
+        const uint8_t* image = L.images + (int64_t)img * L.H * L.Wimg;
+        for (int e = threadIdx.x; e < per; e += blockDim.x) {
+            int r, c;
+            bool masked;
+            if (e < na) {
+                const int rr = e / w3, cc = e - rr * w3;
+                r = r0 - W + rr;
+                c = c0 - W + cc;
+                masked = cc >= w3 - L.mask_w;
+            } else {
+                const int e2 = e - na;
+                const int rr = e2 / W, cc = e2 - rr * W;
+                r = r0 + rr;
+                c = c0 - W + cc;
+                masked = rr >= 2 * W - L.mask_h;
+            }
+            float v = 0.f;
+            if (!masked && r >= 0 && r < L.H && c >= 0 && c < L.Wimg) v = (float)image[r * L.Wimg + c] - L.mean;
+            if (e < na) act_store<SPLIT>(L.above, i * L.pitch_above + e, v);
+            else act_store<SPLIT>(L.left, i * L.pitch_left + (e - na), v);
         }
     }
 }
 
 int launch_gather_image(const GatherLaunch& L, cudaStream_t stream) {
-    const int64_t total = L.n * 5 * L.W * L.W;
-    if (total == 0) return 0;
-    if (L.split) gather_image_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(L);
-    else gather_image_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(L);
+    if (L.n == 0) return 0;
+    const dim3 block(64, 4);
+    const int grid = grid_for(L.n * 64, 64);   // one (64-thread) row per target patch
+    if (L.split) gather_image_kernel<true><<<grid, block, 0, stream>>>(L);
+    else gather_image_kernel<false><<<grid, block, 0, stream>>>(L);
     return 1;
 }
 
@@ -117,39 +113,90 @@ int launch_convert_input(const float* src, Act dst, int64_t n, int split, cudaSt
 // (reference pnn/components.py:33-46, pnn/tfutils.py:134-139).  One thread per output value, the
 // output channel fastest so that the k*k input pixels are warp broadcasts and the stores coalesce.
 // ---------------------------------------------------------------------------------------------
-template <bool SPLIT>
-__global__ void conv0_kernel(Conv0Launch L) {
-    const int64_t per = (int64_t)L.OH * L.OW * L.Cout;
-    const int64_t total = L.n * per;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int co = (int)(idx % L.Cout);
-        int64_t pix = idx / L.Cout;
-        const int ox = (int)(pix % L.OW);
-        pix /= L.OW;
-        const int oy = (int)(pix % L.OH);
-        const int64_t b = pix / L.OH;
-        const float* in = L.in + b * L.IH * L.IW;
-        float acc = 0.f;
-        for (int ky = 0; ky < L.k; ++ky) {
-            const int iy = oy * L.stride + ky - L.pad;
-            if (iy < 0 || iy >= L.IH) continue;
-            for (int kx = 0; kx < L.k; ++kx) {
-                const int ix = ox * L.stride + kx - L.pad;
-                if (ix < 0 || ix >= L.IW) continue;
-                acc = fmaf(in[iy * L.IW + ix], L.w[(ky * L.k + kx) * L.Cout + co], acc);
-            }
+// v2: a CTA of 256 threads computes 64 output pixels x all output channels of one sample; thread =
+// (pixel, group of Cout/4 channels).  The k*k input pixels are read once into registers, the weights sit in
+// shared memory (the 4 channel groups of a warp read 4 distinct 16-byte words: conflict-free broadcasts),
+// and each thread stores its channels with 16-byte vectors.
+template <bool SPLIT, int CPT /*channels per thread*/, int KK /*k*k*/>
+__global__ void __launch_bounds__(256) conv0_kernel(Conv0Launch L) {
+    __shared__ float w_s[KK * CPT * 4];
+    __shared__ float b_s[CPT * 4];
+    const int Cout = CPT * 4;
+    for (int i = threadIdx.x; i < KK * Cout; i += 256) w_s[i] = L.w[i];
+    if (threadIdx.x < Cout) b_s[threadIdx.x] = L.bias[threadIdx.x];
+    __syncthreads();
+    const int P = L.OH * L.OW;
+    const int tiles = (P + 63) >> 6;
+    const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
+    const int pix = (tile << 6) + (threadIdx.x >> 2);
+    const int cg = threadIdx.x & 3;
+    if (pix >= P) return;
+    const int oy = pix / L.OW, ox = pix - oy * L.OW;
+    const float* in = L.in + (int64_t)b * L.IH * L.IW;
+    const int k = L.k;
+    float x[KK];
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        const int ky = t / k, kx = t - ky * k;      // k is 3 or 5: KK is a compile-time 9 or 25
+        const int iy = oy * L.stride + ky - L.pad, ix = ox * L.stride + kx - L.pad;
+        x[t] = (iy >= 0 && iy < L.IH && ix >= 0 && ix < L.IW) ? __ldg(in + iy * L.IW + ix) : 0.f;
+    }
+    float acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        const float4* wr = (const float4*)(w_s + t * Cout + cg * CPT);
+#pragma unroll
+        for (int q = 0; q < CPT / 4; ++q) {
+            const float4 w4 = wr[q];
+            acc[4 * q + 0] = fmaf(x[t], w4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(x[t], w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(x[t], w4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(x[t], w4.w, acc[4 * q + 3]);
         }
-        act_store<SPLIT>(L.out, idx, leaky_relu(acc + L.bias[co]));
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = leaky_relu(acc[j] + b_s[cg * CPT + j]);
+    const int64_t o = ((int64_t)b * P + pix) * Cout + cg * CPT;
+    if (SPLIT) {
+        uint32_t hi[CPT / 2], lo[CPT / 2];
+#pragma unroll
+        for (int j = 0; j < CPT / 2; ++j) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(acc[2 * j], h0, l0);
+            split_bf16(acc[2 * j + 1], h1, l1);
+            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        uint4* ph = (uint4*)((__nv_bfloat16*)L.out.p0 + o);
+        uint4* pl = (uint4*)((__nv_bfloat16*)L.out.p1 + o);
+#pragma unroll
+        for (int q = 0; q < CPT / 8; ++q) {
+            ph[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            pl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        }
+    } else {
+        float4* po = (float4*)((float*)L.out.p0 + o);
+#pragma unroll
+        for (int q = 0; q < CPT / 4; ++q) po[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     }
 }
 
-int launch_conv0(const Conv0Launch& L, cudaStream_t stream) {
-    const int64_t total = (int64_t)L.n * L.OH * L.OW * L.Cout;
-    if (total == 0) return 0;
-    if (L.split) conv0_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(L);
-    else conv0_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(L);
+template <bool SPLIT>
+static int launch_conv0_t(const Conv0Launch& L, cudaStream_t stream) {
+    const int P = L.OH * L.OW;
+    const int64_t grid = (int64_t)L.n * ((P + 63) / 64);
+    if (L.Cout == 64 && L.k == 5) conv0_kernel<SPLIT, 16, 25><<<(unsigned)grid, 256, 0, stream>>>(L);
+    else if (L.Cout == 32 && L.k == 3) conv0_kernel<SPLIT, 8, 9><<<(unsigned)grid, 256, 0, stream>>>(L);
+    else return -1;
     return 1;
+}
+
+int launch_conv0(const Conv0Launch& L, cudaStream_t stream) {
+    if (L.n == 0) return 0;
+    // reference pnn/PredictionNeuralNetwork.py:126-132: the first stride is 2 (k = 5, 64 maps) except for W = 4 (k = 3, 32 maps)
+    return L.split ? launch_conv0_t<true>(L, stream) : launch_conv0_t<false>(L, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -158,35 +205,53 @@ int launch_conv0(const Conv0Launch& L, cudaStream_t stream) {
 // the 32 values of the left map are fully connected to 16 outputs.  One thread per (sample, channel),
 // channel fastest; the weights were transposed on the host to [80][16][C] so that loads coalesce.
 // ---------------------------------------------------------------------------------------------
+// v2: thread = (channel, 4 consecutive samples): every weight load feeds 4 FMAs.
 template <bool SPLIT>
-__global__ void merger_kernel(MergerLaunch L) {
-    const int64_t total = (int64_t)L.n * L.C;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % L.C);
-        const int64_t b = idx / L.C;
-        float acc[16];
+__global__ void __launch_bounds__(128) merger_kernel(MergerLaunch L) {
+    constexpr int SPT = 4;
+    const int cblocks = (L.C + 127) >> 7;
+    const int sgrp = blockIdx.x / cblocks, cb = blockIdx.x - sgrp * cblocks;
+    const int c = (cb << 7) + threadIdx.x;
+    if (c >= L.C) return;
+    const int b0 = sgrp * SPT;
+    float acc[SPT][16];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) acc[p] = 0.f;
-        for (int q = 0; q < 80; ++q) {
-            const float x = q < 48 ? act_load<SPLIT>(L.in0, (b * 48 + q) * L.C + c)
-                                   : act_load<SPLIT>(L.in1, (b * 32 + (q - 48)) * L.C + c);
-            const float* w = L.w + (int64_t)q * 16 * L.C + c;
+    for (int s = 0; s < SPT; ++s)
 #pragma unroll
-            for (int p = 0; p < 16; ++p) acc[p] = fmaf(x, w[p * L.C], acc[p]);
+        for (int p = 0; p < 16; ++p) acc[s][p] = 0.f;
+    for (int q = 0; q < 80; ++q) {
+        float x[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            const int64_t b = b0 + s;
+            x[s] = b < L.n ? (q < 48 ? act_load<SPLIT>(L.in0, (b * 48 + q) * L.C + c)
+                                      : act_load<SPLIT>(L.in1, (b * 32 + (q - 48)) * L.C + c))
+                           : 0.f;
         }
+        const float* w = L.w + q * 16 * L.C + c;
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
-            act_store<SPLIT>(L.out, (b * 16 + p) * L.C + c, leaky_relu(acc[p] + L.bias[p * L.C + c]));
+            const float wv = __ldg(w + p * L.C);
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) acc[s][p] = fmaf(x[s], wv, acc[s][p]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        const int64_t b = b0 + s;
+        if (b >= L.n) break;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            act_store<SPLIT>(L.out, (b * 16 + p) * L.C + c, leaky_relu(acc[s][p] + __ldg(L.bias + p * L.C + c)));
         }
     }
 }
 
 int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
-    const int64_t total = (int64_t)L.n * L.C;
-    if (total == 0) return 0;
-    if (L.split) merger_kernel<true><<<grid_for(total, 128), 128, 0, stream>>>(L);
-    else merger_kernel<false><<<grid_for(total, 128), 128, 0, stream>>>(L);
+    if (L.n == 0) return 0;
+    const int64_t grid = (int64_t)((L.n + 3) / 4) * ((L.C + 127) / 128);
+    if (L.split) merger_kernel<true><<<(unsigned)grid, 128, 0, stream>>>(L);
+    else merger_kernel<false><<<(unsigned)grid, 128, 0, stream>>>(L);
     return 1;
 }
 
@@ -197,63 +262,68 @@ int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
 //   out[y, x] = bias + sum_{ky,kx : (y+pad-ky) % s == 0 ...} in[(y+pad-ky)/s, (x+pad-kx)/s, :] . w[ky, kx, :]
 // One thread per output pixel.
 // ---------------------------------------------------------------------------------------------
+// v2: one CTA per (sample, 128 output pixels), weights in shared memory, 32-bit index arithmetic.
 template <bool SPLIT>
-__global__ void tconv_last_kernel(TconvLastLaunch L) {
-    const int OH = L.IH * L.stride, OW = L.IW * L.stride;
-    const int64_t total = (int64_t)L.n * OH * OW;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % OW);
-        const int y = (int)((idx / OW) % OH);
-        const int64_t b = idx / ((int64_t)OW * OH);
-        float acc = 0.f;
-        for (int ky = 0; ky < L.k; ++ky) {
-            const int ty = y + L.pad - ky;
-            if (ty < 0 || ty % L.stride) continue;
-            const int iy = ty / L.stride;
-            if (iy >= L.IH) continue;
-            for (int kx = 0; kx < L.k; ++kx) {
-                const int tx = x + L.pad - kx;
-                if (tx < 0 || tx % L.stride) continue;
-                const int ix = tx / L.stride;
-                if (ix >= L.IW) continue;
-                const int64_t base = ((b * L.IH + iy) * L.IW + ix) * L.Cin;
-                const float* w = L.w + (ky * L.k + kx) * L.Cin;
-                if (SPLIT) {
-                    const uint4* ph = (const uint4*)((const __nv_bfloat16*)L.in.p0 + base);
-                    const uint4* pl = (const uint4*)((const __nv_bfloat16*)L.in.p1 + base);
-                    for (int ci = 0; ci < L.Cin; ci += 8) {
-                        const uint4 h = ph[ci >> 3], l = pl[ci >> 3];
-                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+__global__ void __launch_bounds__(128) tconv_last_kernel(TconvLastLaunch L) {
+    extern __shared__ float w_s[];                       // [k*k][Cin]
+    for (int i = threadIdx.x; i < L.k * L.k * L.Cin; i += 128) w_s[i] = L.w[i];
+    __syncthreads();
+    const int OH = L.IH * L.stride, OW = L.IW * L.stride, P = OH * OW;
+    const int tiles = (P + 127) >> 7;
+    const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
+    const int pix = (tile << 7) + threadIdx.x;
+    if (pix >= P) return;
+    const int y = pix / OW, x = pix - y * OW;
+    const int64_t in_base = (int64_t)b * L.IH * L.IW * L.Cin;
+    float acc = 0.f;
+    for (int ky = 0; ky < L.k; ++ky) {
+        const int ty = y + L.pad - ky;
+        if (ty < 0 || (L.stride == 2 && (ty & 1))) continue;
+        const int iy = L.stride == 2 ? ty >> 1 : ty;
+        if (iy >= L.IH) continue;
+        for (int kx = 0; kx < L.k; ++kx) {
+            const int tx = x + L.pad - kx;
+            if (tx < 0 || (L.stride == 2 && (tx & 1))) continue;
+            const int ix = L.stride == 2 ? tx >> 1 : tx;
+            if (ix >= L.IW) continue;
+            const int64_t base = in_base + (int64_t)(iy * L.IW + ix) * L.Cin;
+            const float* w = w_s + (ky * L.k + kx) * L.Cin;
+            if (SPLIT) {
+                const uint4* ph = (const uint4*)((const __nv_bfloat16*)L.in.p0 + base);
+                const uint4* pl = (const uint4*)((const __nv_bfloat16*)L.in.p1 + base);
+                for (int ci = 0; ci < L.Cin; ci += 8) {
+                    const uint4 h = __ldg(ph + (ci >> 3)), l = __ldg(pl + (ci >> 3));
+                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float a0 = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                            const float a1 = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
-                            acc = fmaf(a0, w[ci + 2 * j], acc);
-                            acc = fmaf(a1, w[ci + 2 * j + 1], acc);
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        const float a0 = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                        const float a1 = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+                        acc = fmaf(a0, w[ci + 2 * j], acc);
+                        acc = fmaf(a1, w[ci + 2 * j + 1], acc);
                     }
-                } else {
-                    const float4* p = (const float4*)((const float*)L.in.p0 + base);
-                    for (int ci = 0; ci < L.Cin; ci += 4) {
-                        const float4 a = p[ci >> 2];
-                        acc = fmaf(a.x, w[ci], acc);
-                        acc = fmaf(a.y, w[ci + 1], acc);
-                        acc = fmaf(a.z, w[ci + 2], acc);
-                        acc = fmaf(a.w, w[ci + 3], acc);
-                    }
+                }
+            } else {
+                const float4* p = (const float4*)((const float*)L.in.p0 + base);
+                for (int ci = 0; ci < L.Cin; ci += 4) {
+                    const float4 a = __ldg(p + (ci >> 2));
+                    acc = fmaf(a.x, w[ci], acc);
+                    acc = fmaf(a.y, w[ci + 1], acc);
+                    acc = fmaf(a.z, w[ci + 2], acc);
+                    acc = fmaf(a.w, w[ci + 3], acc);
                 }
             }
         }
-        final_store(L.fin, idx, acc + L.bias);
     }
+    final_store(L.fin, (int64_t)b * P + pix, acc + L.bias);
 }
 
 int launch_tconv_last(const TconvLastLaunch& L, cudaStream_t stream) {
-    const int64_t total = (int64_t)L.n * L.IH * L.stride * L.IW * L.stride;
-    if (total == 0) return 0;
-    if (L.split) tconv_last_kernel<true><<<grid_for(total, 128), 128, 0, stream>>>(L);
-    else tconv_last_kernel<false><<<grid_for(total, 128), 128, 0, stream>>>(L);
+    if (L.n == 0) return 0;
+    const int P = L.IH * L.stride * L.IW * L.stride;
+    const int64_t grid = (int64_t)L.n * ((P + 127) / 128);
+    const size_t smem = (size_t)L.k * L.k * L.Cin * sizeof(float);
+    if (L.split) tconv_last_kernel<true><<<(unsigned)grid, 128, smem, stream>>>(L);
+    else tconv_last_kernel<false><<<(unsigned)grid, 128, smem, stream>>>(L);
     return 1;
 }
 
