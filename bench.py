@@ -37,6 +37,18 @@ METRIC = 'PNN predictions/sec (4x4+8x8+16x16+32x32 blocks, 100 BSDS-shaped image
 MACS = {4: 2995200, 8: 3340800, 16: 48750592, 32: 273317888}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    text = json.dumps(line) + '\n'
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text.encode())
+
+
 def synthetic_image(height, width, seed):
     """clip(128 + 60 sin(x/17) + 40 cos(y/11) + N(0, 4^2)), default_rng(seed)."""
     rng = numpy.random.default_rng(seed)
@@ -182,7 +194,7 @@ def run_reference(args, rank):
         'e2e': {'value': value, 'unit': 'predictions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': time.perf_counter() - t_all,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -199,12 +211,18 @@ def main():
     ap.add_argument('--cpu-baseline-seconds', type=float, default=4.0)
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--skip-e2e', action='store_true', help='profiling runs only: skip the host-buffer arm')
     ap.add_argument('--report', action='store_true', help='print the per-kernel table to stderr')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    # libraries (NCCL's version banner) write to fd 1; keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    global _JSON_FD
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
     if args.impl == 'reference':
         run_reference(args, rank)
@@ -330,11 +348,11 @@ def main():
     value = world * total / (ms_per_step * 1e-3)
 
     # ---- end-to-end arm (host buffers through the C ABI) -----------------------------------------
-    for _ in range(2):
+    for _ in range(0 if args.skip_e2e else 2):
         step_e2e()
     barrier()
     walls = []
-    for _ in range(args.steps):
+    for _ in range(1 if args.skip_e2e else args.steps):
         barrier()
         tw = time.perf_counter()
         stats = step_e2e()
@@ -395,7 +413,7 @@ def main():
             }
         if args.report:
             sys.stderr.write(prof['text'] + '\n')
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
