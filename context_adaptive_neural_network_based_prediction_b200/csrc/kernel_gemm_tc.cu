@@ -9,30 +9,35 @@
 // (k ascending, the three products in the order above), no atomics, no split-K: the same inputs
 // give the same bits in the encoder and in the decoder.
 //
-// Tile: 128 rows (UMMA_M = 128, cta_group::1) x up to 256 columns (UMMA_N = tile width) x 64 K per stage.
-// Warp roles (192 threads):
+// Persistent kernel: one CTA per SM, tiles (128 rows x up to 256 columns) taken round-robin
+// (tile = blockIdx.x + i*gridDim.x, n-tile fastest so that concurrent CTAs share the A rows in L2).
+// Warp roles (320 threads):
 //   warps 0-3  A producers: implicit-GEMM gather of 16-byte (8-channel) chunks with cp.async straight
 //              into the 128-byte-swizzled K-major shared-memory layout, zero-filling SAME padding,
 //              transposed-convolution borders, K tails and M tails; completion is signalled with
-//              cp.async.mbarrier.arrive.noinc.  After the main loop the same warps run the epilogue:
-//              tcgen05.ld -> bias -> LeakyReLU -> hi/lo split -> 16-byte stores (or the final epilogue).
+//              cp.async.mbarrier.arrive.noinc.
 //   warp 4     B producer: one cp.async.bulk per stage; the weights were pre-tiled on the host as the
 //              exact shared-memory image (hi plane then lo plane), so no tensor map is needed.
-//   warp 5     TMEM allocation + single-thread MMA issue; tcgen05.commit frees the stage / publishes
-//              the accumulator.
+//   warp 5     TMEM allocation (512 columns = two accumulators) + single-thread MMA issue;
+//              tcgen05.commit frees the smem stage / publishes the accumulator.
+//   warps 6-9  epilogue of tile i while the main loop of tile i+1 runs on the other accumulator:
+//              tcgen05.ld -> bias -> LeakyReLU -> hi/lo split -> swizzled staging in shared memory ->
+//              16-byte global stores where 8 consecutive lanes cover 128 contiguous bytes of one row
+//              (or the final epilogue: raw fp32 + add-mean / clip / round).
+// The smem ring has 2-4 stages depending on the tile width (A 32 KB + B 2*bn*128 B per stage).
 #include "kernels_common.cuh"
 
 namespace pnn {
 
 namespace {
 
-constexpr int STAGES = 2;
+constexpr int MAX_STAGES = 4;
 constexpr int A_PLANE = TC_BM * 128;                 // 16 KB
-constexpr int B_PLANE_MAX = TC_BN * 128;             // 32 KB
-constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE_MAX;   // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 256;
+constexpr int RING_BYTES = 2 * (2 * A_PLANE + 2 * TC_BN * 128);   // 192 KB: 2 stages at bn = 256, 3 at 128, 4 at <= 64
+constexpr int STAGING_BYTES = 4 * 8192;              // per epilogue warp: 32 rows x 128 B, hi and lo
+constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 320;
+constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -77,14 +82,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
@@ -99,33 +110,48 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// element offset of output row m (pixel (b, oy, ox) of this launch's phase) in the NHWC output
+__device__ __forceinline__ int64_t out_row_offset(const GemmGeom& g, int m) {
+    const int b = m / g.P, p = m - b * g.P;
+    const int oy = p / g.OW, ox = p - oy * g.OW;
+    return (int64_t)b * g.out_sample_stride + ((int64_t)(oy * g.osy + g.ooy) * g.OWf + (ox * g.osx + g.oox)) * g.N;
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     const GemmGeom& g = L.g;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-    // barrier slots (8 B each): full_a[s], full_b[s], empty[s], tmem_full; then the TMEM base address
+    const uint32_t staging = smem_base + RING_BYTES;
+    const uint32_t bars = staging + STAGING_BYTES;
+    // barrier slots (8 B each)
     auto full_a = [&](int s) { return bars + 8u * s; };
-    auto full_b = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-    const uint32_t tmem_full = bars + 8u * (3 * STAGES);
-    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);
+    auto full_b = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * MAX_STAGES + s); };
+    auto tmem_full = [&](int a) { return bars + 8u * (3 * MAX_STAGES + a); };
+    auto tmem_empty = [&](int a) { return bars + 8u * (3 * MAX_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (3 * MAX_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_nt = (g.N + TC_BN - 1) / TC_BN;
-    const int nt = blockIdx.x % num_nt, mt = blockIdx.x / num_nt;
-    const int m0 = mt * TC_BM, n0 = nt * TC_BN;
-    int bn = g.N - n0;
-    bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
+    const int num_mt = (L.M + TC_BM - 1) / TC_BM;
+    const int num_tiles = num_nt * num_mt;
     const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+    // the widest tile fixes the stage size, hence the ring depth
+    const int bn_max = g.N >= TC_BN ? TC_BN : ((g.N + 15) & ~15);
+    const uint32_t stage_bytes = 2u * A_PLANE + 2u * (uint32_t)bn_max * 128u;
+    int num_stages = RING_BYTES / stage_bytes;
+    if (num_stages > MAX_STAGES) num_stages = MAX_STAGES;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(full_a(s), 128);
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -144,142 +170,224 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
         const int c = threadIdx.x & 7;          // 16-byte chunk (8 channels) inside the 64-wide k block
         const int rgrp = threadIdx.x >> 3;      // rows rgrp + 16*i
         const uint32_t sw = (uint32_t)((c ^ (rgrp & 7)) << 4);
-        int64_t rbase[8];
-        int rpos[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + rgrp + 16 * i;
-            if (m < L.M) {
-                const int b = m / g.P, p = m - b * g.P;
-                const int oy = p / g.OW, ox = p - oy * g.OW;
-                rbase[i] = (int64_t)b * g.in_sample_stride;
-                rpos[i] = (oy << 16) | ox;
-            } else {
-                rbase[i] = 0;
-                rpos[i] = -1;
-            }
-        }
         const __nv_bfloat16* in_hi = (const __nv_bfloat16*)L.in.p0;
         const __nv_bfloat16* in_lo = (const __nv_bfloat16*)L.in.p1;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t round = (uint32_t)(kb / STAGES);
-            mbar_wait(empty(s), (round & 1u) ^ 1u);
-            const int k = kb * TC_BK + c * 8;
-            const bool k_ok = k < g.K;
-            const int tap = k / g.Cin, ci = k - tap * g.Cin;
-            const int ty = tap / g.TW, tx = tap - ty * g.TW;
-            const int dy = ty * g.sy_t + g.cy, dx = tx * g.sx_t + g.cx;
-            const uint32_t a_hi = smem_base + s * STAGE_BYTES + sw;
-            const uint32_t a_lo = a_hi + A_PLANE;
+        int s = 0;
+        uint32_t ph = 0;
+        int cur_mt = -1;
+        int64_t rbase[8];
+        int rpos[8];
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / num_nt;
+            if (mt != cur_mt) {
+                cur_mt = mt;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int oy = rpos[i] >> 16, ox = rpos[i] & 0xffff;
-                const int iy = oy * g.sy_o + dy, ix = ox * g.sx_o + dx;
-                const bool ok = k_ok && rpos[i] >= 0 && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
-                const int64_t off = ok ? rbase[i] + ((int64_t)iy * g.IW + ix) * g.Cin + ci : 0;
-                const uint32_t row_off = (uint32_t)(rgrp + 16 * i) * 128u;
-                cp_async_16(a_hi + row_off, in_hi + off, ok ? 16u : 0u);
-                cp_async_16(a_lo + row_off, in_lo + off, ok ? 16u : 0u);
-            }
-            cp_async_arrive_noinc(full_a(s));
-        }
-
-        // ------------------------------------------------------------------ epilogue
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = warp * 32 + lane;
-        const int m = m0 + row;
-        const bool row_ok = m < L.M;
-        int64_t obase = 0;
-        if (row_ok) {
-            const int b = m / g.P, p = m - b * g.P;
-            const int oy = p / g.OW, ox = p - oy * g.OW;
-            obase = (int64_t)b * g.out_sample_stride +
-                    ((int64_t)(oy * g.osy + g.ooy) * g.OWf + (ox * g.osx + g.oox)) * g.N;
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int cg = 0; cg < bn / 16; ++cg) {
-            uint32_t v[16];
-            tmem_ld16(taddr + cg * 16, v);
-            const int n = n0 + cg * 16;
-            if (!row_ok || n >= g.N) continue;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                f[j] = __uint_as_float(v[j]) + __ldg(L.bias + n + j);
-                if (g.leaky) f[j] = leaky_relu(f[j]);
-            }
-            if (L.out_mode == OUT_FINAL) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) final_store(L.fin, obase + n + j, f[j]);
-            } else {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(f[2 * j], h0, l0);
-                    split_bf16(f[2 * j + 1], h1, l1);
-                    hi[j] = pack_bf16(h0, h1);
-                    lo[j] = pack_bf16(l0, l1);
+                for (int i = 0; i < 8; ++i) {
+                    const int m = mt * TC_BM + rgrp + 16 * i;
+                    if (m < L.M) {
+                        const int b = m / g.P, p = m - b * g.P;
+                        const int oy = p / g.OW, ox = p - oy * g.OW;
+                        rbase[i] = (int64_t)b * g.in_sample_stride;
+                        rpos[i] = (oy << 16) | ox;
+                    } else {
+                        rbase[i] = 0;
+                        rpos[i] = -1;
+                    }
                 }
-                uint4* ph = (uint4*)((__nv_bfloat16*)L.out.p0 + obase + n);
-                uint4* pl = (uint4*)((__nv_bfloat16*)L.out.p1 + obase + n);
-                ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                ph[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                pl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+            }
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty(s), ph ^ 1u);
+                const int k = kb * TC_BK + c * 8;
+                const bool k_ok = k < g.K;
+                const int tap = k / g.Cin, ci = k - tap * g.Cin;
+                const int ty = tap / g.TW, tx = tap - ty * g.TW;
+                const int dy = ty * g.sy_t + g.cy, dx = tx * g.sx_t + g.cx;
+                const uint32_t a_hi = smem_base + s * stage_bytes + sw;
+                const uint32_t a_lo = a_hi + A_PLANE;
+                if (!(L.debug_flags & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int oy = rpos[i] >> 16, ox = rpos[i] & 0xffff;
+                        const int iy = oy * g.sy_o + dy, ix = ox * g.sx_o + dx;
+                        const bool ok = k_ok && rpos[i] >= 0 && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
+                        const int64_t off = ok ? rbase[i] + ((int64_t)iy * g.IW + ix) * g.Cin + ci : 0;
+                        const uint32_t row_off = (uint32_t)(rgrp + 16 * i) * 128u;
+                        cp_async_16(a_hi + row_off, in_hi + off, ok ? 16u : 0u);
+                        cp_async_16(a_lo + row_off, in_lo + off, ok ? 16u : 0u);
+                    }
+                }
+                cp_async_arrive_noinc(full_a(s));
+                if (++s == num_stages) { s = 0; ph ^= 1u; }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else if (warp == 4) {
         // ------------------------------------------------------------------ B producer
         if (lane == 0) {
-            const uint32_t stage_b_bytes = 2u * (uint32_t)bn * 128u;
-            const uint8_t* src = L.w_tiles + (size_t)nt * num_kb * (2u * TC_BN * 128u);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % num_nt;
+                int bn = g.N - nt * TC_BN;
+                bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
+                const uint32_t b_bytes = 2u * (uint32_t)bn * 128u;
+                const uint8_t* src = L.w_tiles + (size_t)nt * num_kb * (2u * TC_BN * 128u);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty(s), ph ^ 1u);
+                    if (L.debug_flags & 2) {
+                        mbar_arrive(full_b(s));
+                    } else {
+                        mbar_arrive_expect_tx(full_b(s), b_bytes);
+                        bulk_copy_g2s(smem_base + s * stage_bytes + 2 * A_PLANE, src + (size_t)kb * b_bytes, b_bytes, full_b(s));
+                    }
+                    if (++s == num_stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer
+        int s = 0;
+        uint32_t ph = 0;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int nt = tile % num_nt;
+            int bn = g.N - nt * TC_BN;
+            bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
+            // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
+            // N >> 3 in [17,23), M >> 4 in [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const int ab = lt & 1;
+            const uint32_t acc = tmem_base + (uint32_t)(ab * TC_BN);
+            mbar_wait(tmem_empty(ab), (((uint32_t)lt >> 1) & 1u) ^ 1u);     // the epilogue drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t round = (uint32_t)(kb / STAGES);
-                mbar_wait(empty(s), (round & 1u) ^ 1u);
-                mbar_arrive_expect_tx(full_b(s), stage_b_bytes);
-                bulk_copy_g2s(smem_base + s * STAGE_BYTES + 2 * A_PLANE, src + (size_t)kb * stage_b_bytes, stage_b_bytes,
-                              full_b(s));
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    // cp.async (generic proxy) wrote the A tiles; order them before the tensor core's
+                    // async-proxy reads
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t a_hi = smem_base + s * stage_bytes;
+                    const uint32_t a_lo = a_hi + A_PLANE;
+                    const uint32_t b_hi = a_hi + 2 * A_PLANE;
+                    const uint32_t b_lo = b_hi + (uint32_t)bn * 128u;
+                    // 16-wide K steps that hold data (the K tail of the last block is skipped, not multiplied by zero)
+                    int ksteps = (g.K - kb * TC_BK + 15) >> 4;
+                    if (ksteps > TC_BK / 16) ksteps = TC_BK / 16;
+                    for (int k4 = 0; k4 < ksteps; ++k4) {
+                        const uint64_t da_hi = make_desc(a_hi + k4 * 32), da_lo = make_desc(a_lo + k4 * 32);
+                        const uint64_t db_hi = make_desc(b_hi + k4 * 32), db_lo = make_desc(b_lo + k4 * 32);
+                        umma_bf16(acc, da_hi, db_hi, idesc, (kb | k4) != 0 ? 1u : 0u);
+                        umma_bf16(acc, da_hi, db_lo, idesc, 1u);
+                        umma_bf16(acc, da_lo, db_hi, idesc, 1u);
+                    }
+                    umma_commit(empty(s));
+                    if (kb == num_kb - 1) umma_commit(tmem_full(ab));
+                }
+                __syncwarp();
+                if (++s == num_stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
-        // ------------------------------------------------------------------ MMA issuer
-        // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
-        // N >> 3 in [17,23), M >> 4 in [24,29)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t round = (uint32_t)(kb / STAGES);
-            mbar_wait(full_a(s), round & 1u);
-            mbar_wait(full_b(s), round & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                // cp.async (generic proxy) wrote the A tiles; order them before the tensor core's
-                // async-proxy reads
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                const uint32_t a_hi = smem_base + s * STAGE_BYTES;
-                const uint32_t a_lo = a_hi + A_PLANE;
-                const uint32_t b_hi = a_hi + 2 * A_PLANE;
-                const uint32_t b_lo = b_hi + (uint32_t)bn * 128u;
+        // ------------------------------------------------------------------ epilogue warps (6..9)
+        const int q = warp & 3;                              // TMEM lane quarter this warp may read
+        const uint32_t stg_hi = staging + (uint32_t)(warp - 6) * 8192u;
+        const uint32_t stg_lo = stg_hi + 4096u;
+        const int cchunk = lane & 7;                         // 16-byte chunk of a row segment in the copy-out phase
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            const int nt = tile % num_nt, mt = tile / num_nt;
+            const int n0 = nt * TC_BN;
+            int bn = g.N - n0;
+            bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
+            const int ab = lt & 1;
+            const int row = q * 32 + lane;                   // accumulator row owned in the TMEM-read phase
+            const int m_own = mt * TC_BM + row;
+            // rows this lane copies out: (lane >> 3) + 4*i of the warp's 32 rows
+            int64_t obase[8];
 #pragma unroll
-                for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
-                    const uint64_t da_hi = make_desc(a_hi + k4 * 32), da_lo = make_desc(a_lo + k4 * 32);
-                    const uint64_t db_hi = make_desc(b_hi + k4 * 32), db_lo = make_desc(b_lo + k4 * 32);
-                    umma_bf16(tmem_base, da_hi, db_hi, idesc, (kb | k4) != 0 ? 1u : 0u);
-                    umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
-                    umma_bf16(tmem_base, da_lo, db_hi, idesc, 1u);
-                }
-                umma_commit(empty(s));
-                if (kb == num_kb - 1) umma_commit(tmem_full);
+            for (int i = 0; i < 8; ++i) {
+                const int m = mt * TC_BM + q * 32 + (lane >> 3) + 4 * i;
+                obase[i] = m < L.M ? out_row_offset(g, m) : -1;
             }
+            const int64_t obase_own = m_own < L.M ? out_row_offset(g, m_own) : -1;
+            mbar_wait(tmem_full(ab), ((uint32_t)lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * TC_BN);
+            for (int c0 = 0; c0 < bn; c0 += 64) {
+                uint32_t v[64];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld32(taddr + c0 + 32, v + 32);
+                tmem_ld_wait();
+                const int nbase = n0 + c0;
+                int nvalid = g.N - nbase;                    // multiple of 16 by construction
+                if (nvalid > 64) nvalid = 64;
+                if (L.debug_flags & 4) continue;
+                if (L.out_mode == OUT_FINAL) {
+                    if (obase_own >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) {
+                            if (j < nvalid) {
+                                float f = __uint_as_float(v[j]) + __ldg(L.bias + nbase + j);
+                                if (g.leaky) f = leaky_relu(f);
+                                final_store(L.fin, obase_own + nbase + j, f);
+                            }
+                        }
+                    }
+                    continue;
+                }
+                // bias, LeakyReLU, split, swizzled staging (chunk c of row r at position c ^ (r & 7))
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = ch * 8 + 2 * j;
+                        float f0 = 0.f, f1 = 0.f;
+                        if (col < nvalid) {
+                            f0 = __uint_as_float(v[col]) + __ldg(L.bias + nbase + col);
+                            f1 = __uint_as_float(v[col + 1]) + __ldg(L.bias + nbase + col + 1);
+                            if (g.leaky) {
+                                f0 = leaky_relu(f0);
+                                f1 = leaky_relu(f1);
+                            }
+                        }
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(f0, h0, l0);
+                        split_bf16(f1, h1, l1);
+                        hi[j] = pack_bf16(h0, h1);
+                        lo[j] = pack_bf16(l0, l1);
+                    }
+                    const uint32_t off = (uint32_t)lane * 128u + (uint32_t)((ch ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                }
+                __syncwarp();
+                // copy out: 8 consecutive lanes write the 128 contiguous bytes of one row segment
+                if (cchunk * 8 < nvalid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (obase[i] < 0) continue;
+                        const int r = (lane >> 3) + 4 * i;
+                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cchunk ^ (r & 7)) << 4);
+                        uint4 h, l;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(stg_hi + off));
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(stg_lo + off));
+                        const int64_t o = obase[i] + nbase + cchunk * 8;
+                        *(uint4*)((__nv_bfloat16*)L.out.p0 + o) = h;
+                        *(uint4*)((__nv_bfloat16*)L.out.p1 + o) = l;
+                    }
+                }
+                __syncwarp();
+            }
+            // this warp's TMEM reads of the tile are done: hand the accumulator back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(ab));
         }
     }
 
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 5) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -293,11 +401,21 @@ cudaError_t gemm_tc_init() {
     return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
+static int g_num_sms = 0;
+
 int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) {
     if (L.M == 0) return 0;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
     const int num_nt = (L.g.N + TC_BN - 1) / TC_BN;
     const int num_mt = (L.M + TC_BM - 1) / TC_BM;
-    gemm_tc_kernel<<<num_nt * num_mt, NUM_THREADS, SMEM_BYTES, stream>>>(L);
+    const long long tiles = (long long)num_nt * num_mt;
+    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);   // persistent: one CTA per SM
+    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(L);
     return 1;
 }
 

@@ -884,6 +884,47 @@ const char* pnn_profile_report(pnn_handle* h, double* gemm_ms, double* gemm_flop
     return h->prof_text.c_str();
 }
 
+float pnn_debug_time_gemm(pnn_handle* h, int64_t M, int N, int K, int iters, int flags) {
+    if (!h) return -1.f;
+    try {
+        if (M <= 0 || N <= 0 || K <= 0 || N % 16 || K % 8 || iters <= 0) throw std::runtime_error("bad problem size");
+        CUDA_TRY(cudaSetDevice(h->device));
+        DevBuf a_hi, a_lo, o_hi, o_lo, wt, bias;
+        a_hi.reserve((size_t)M * K * 2);
+        a_lo.reserve((size_t)M * K * 2);
+        o_hi.reserve((size_t)M * N * 2);
+        o_lo.reserve((size_t)M * N * 2);
+        wt.reserve(tc_total_bytes(N, K));
+        bias.reserve((size_t)N * 4);
+        CUDA_TRY(cudaMemset(a_hi.p, 0, (size_t)M * K * 2));
+        CUDA_TRY(cudaMemset(a_lo.p, 0, (size_t)M * K * 2));
+        CUDA_TRY(cudaMemset(wt.p, 0, tc_total_bytes(N, K)));
+        CUDA_TRY(cudaMemset(bias.p, 0, (size_t)N * 4));
+        GemmLaunch L{};
+        GemmGeom& g = L.g;
+        g.P = 1; g.OW = 1; g.Cin = K; g.TH = 1; g.TW = 1; g.IH = 1; g.IW = 1;
+        g.in_sample_stride = K; g.N = N; g.K = K; g.OHf = 1; g.OWf = 1; g.osy = 1; g.osx = 1;
+        g.out_sample_stride = N; g.leaky = 1;
+        L.in.p0 = a_hi.p; L.in.p1 = a_lo.p; L.out.p0 = o_hi.p; L.out.p1 = o_lo.p;
+        L.out_mode = OUT_ACT; L.M = (int)M; L.w_tiles = (const uint8_t*)wt.p; L.bias = (const float*)bias.p;
+        L.debug_flags = flags;
+        cudaStream_t s = h->stream;
+        launch_gemm_tc(L, s);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaEventRecord(h->ev0, s));
+        for (int i = 0; i < iters; ++i) launch_gemm_tc(L, s);
+        CUDA_TRY(cudaEventRecord(h->ev1, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaGetLastError());
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        return ms / iters;
+    } catch (const std::exception& e) {
+        fail(h, e);
+        return -1.f;
+    }
+}
+
 int64_t pnn_launch_count(pnn_handle* h) { return h ? h->launches : 0; }
 
 float pnn_last_hm_device_ms(pnn_handle* h) { return h ? h->hm_ms : 0.f; }

@@ -62,6 +62,7 @@ struct GemmLaunch {
     const float* w_fp32;        // [K][N] fp32 (fp32 precision)
     const uint8_t* w_tiles;     // pre-swizzled bf16 hi/lo tiles (bf16x3 precision)
     const float* bias;          // [N]
+    int debug_flags;            // tuning aid: bit 0 skip A loads, bit 1 skip B loads, bit 2 skip epilogue stores
 };
 
 // bf16x3 weight tiling (see DESIGN.md "weight tiles"): N is cut in tiles of TC_BN rows (the last one

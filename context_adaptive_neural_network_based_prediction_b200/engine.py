@@ -80,6 +80,13 @@ class Engine(object):
     def win_flags_device(self, d_psnr, d_baseline, n, d_win, stream=0):
         self._check(self._lib.pnn_win_flags_device(self._h, d_psnr, d_baseline, n, d_win, stream))
 
+    def time_gemm(self, m, n, k, iters=5, flags=0):
+        """Tuning aid: mean ms per launch of the tcgen05 GEMM kernel on a synthetic [m,k]x[k,n] problem."""
+        ms = float(self._lib.pnn_debug_time_gemm(self._h, m, n, k, iters, flags))
+        if ms < 0:
+            raise PnnError(self._lib.pnn_last_error(self._h).decode())
+        return ms
+
     def get_activation(self, width_target, is_fully_connected, buffer_index, n_samples):
         """Inspection hook: activation buffer `buffer_index` as left by the last call, float32 [n, elems]."""
         per = ctypes.c_int64()

@@ -158,6 +158,15 @@ const char* pnn_profile_report(pnn_handle* h, double* gemm_ms, double* gemm_flop
 int pnn_debug_get_activation(pnn_handle* h, int width, int is_fully_connected, int buffer_index, int64_t n_samples,
                              float* out, int64_t* elems_per_sample);
 
+/*
+ * Tuning aid (no reference counterpart): times `iters` launches of the tcgen05 GEMM kernel on a synthetic
+ * fully-connected problem out[M,N] = lrelu(in[M,K] * W[K,N] + b) with zero-filled operands and returns the
+ * mean device time per launch in milliseconds (< 0 on error).  `flags`: bit 0 skip the A (activation) loads,
+ * bit 1 skip the B (weight) loads, bit 2 skip the epilogue stores -- results are then meaningless, only the
+ * time is of interest.
+ */
+float pnn_debug_time_gemm(pnn_handle* h, int64_t M, int N, int K, int iters, int flags);
+
 /* Library version string. */
 const char* pnn_version(void);
 
