@@ -314,24 +314,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
             mbar_wait(tmem_full(ab), ((uint32_t)lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * TC_BN);
+            // bias of a 64-column block: two coalesced loads per lane, broadcast by shuffle (prefetched one block ahead)
+            float bias0 = n0 + lane < g.N ? __ldg(L.bias + n0 + lane) : 0.f;
+            float bias1 = n0 + 32 + lane < g.N ? __ldg(L.bias + n0 + 32 + lane) : 0.f;
             for (int c0 = 0; c0 < bn; c0 += 64) {
                 uint32_t v[64];
                 tmem_ld32(taddr + c0, v);
                 tmem_ld32(taddr + c0 + 32, v + 32);
-                tmem_ld_wait();
                 const int nbase = n0 + c0;
+                const float b_lo32 = bias0, b_hi32 = bias1;
+                if (c0 + 64 < bn) {
+                    bias0 = nbase + 64 + lane < g.N ? __ldg(L.bias + nbase + 64 + lane) : 0.f;
+                    bias1 = nbase + 96 + lane < g.N ? __ldg(L.bias + nbase + 96 + lane) : 0.f;
+                }
+                tmem_ld_wait();
                 int nvalid = g.N - nbase;                    // multiple of 16 by construction
                 if (nvalid > 64) nvalid = 64;
                 if (L.debug_flags & 4) continue;
                 if (L.out_mode == OUT_FINAL) {
-                    if (obase_own >= 0) {
 #pragma unroll
-                        for (int j = 0; j < 64; ++j) {
-                            if (j < nvalid) {
-                                float f = __uint_as_float(v[j]) + __ldg(L.bias + nbase + j);
-                                if (g.leaky) f = leaky_relu(f);
-                                final_store(L.fin, obase_own + nbase + j, f);
-                            }
+                    for (int j = 0; j < 64; ++j) {
+                        const float bj = __shfl_sync(0xffffffffu, j < 32 ? b_lo32 : b_hi32, j & 31);
+                        if (j < nvalid && obase_own >= 0) {
+                            float f = __uint_as_float(v[j]) + bj;
+                            if (g.leaky) f = leaky_relu(f);
+                            final_store(L.fin, obase_own + nbase + j, f);
                         }
                     }
                     continue;
@@ -343,14 +350,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int col = ch * 8 + 2 * j;
-                        float f0 = 0.f, f1 = 0.f;
-                        if (col < nvalid) {
-                            f0 = __uint_as_float(v[col]) + __ldg(L.bias + nbase + col);
-                            f1 = __uint_as_float(v[col + 1]) + __ldg(L.bias + nbase + col + 1);
-                            if (g.leaky) {
-                                f0 = leaky_relu(f0);
-                                f1 = leaky_relu(f1);
-                            }
+                        const float bj0 = __shfl_sync(0xffffffffu, col < 32 ? b_lo32 : b_hi32, col & 31);
+                        const float bj1 = __shfl_sync(0xffffffffu, col < 32 ? b_lo32 : b_hi32, (col + 1) & 31);
+                        float f0 = __uint_as_float(v[col]) + bj0;
+                        float f1 = __uint_as_float(v[col + 1]) + bj1;
+                        if (g.leaky) {
+                            f0 = leaky_relu(f0);
+                            f1 = leaky_relu(f1);
                         }
                         __nv_bfloat16 h0, l0, h1, l1;
                         split_bf16(f0, h0, l0);
@@ -359,8 +365,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
                         lo[j] = pack_bf16(l0, l1);
                     }
                     const uint32_t off = (uint32_t)lane * 128u + (uint32_t)((ch ^ (lane & 7)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
                 }
                 __syncwarp();
                 // copy out: 8 consecutive lanes write the 128 contiguous bytes of one row segment
