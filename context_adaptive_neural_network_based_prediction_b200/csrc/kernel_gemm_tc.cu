@@ -20,10 +20,11 @@
 //              exact shared-memory image (hi plane then lo plane), so no tensor map is needed.
 //   warp 5     TMEM allocation (512 columns = two accumulators) + single-thread MMA issue;
 //              tcgen05.commit frees the smem stage / publishes the accumulator.
-//   warps 6-9  epilogue of tile i while the main loop of tile i+1 runs on the other accumulator:
-//              tcgen05.ld -> bias -> LeakyReLU -> hi/lo split -> swizzled staging in shared memory ->
-//              16-byte global stores where 8 consecutive lanes cover 128 contiguous bytes of one row
-//              (or the final epilogue: raw fp32 + add-mean / clip / round).
+//   warps 8-11 / 12-15  two epilogue sets, one per accumulator, so that the epilogues of tiles i and i+1
+//              and the main loop of tile i+2 overlap: tcgen05.ld -> bias -> LeakyReLU -> hi/lo split ->
+//              swizzled staging in shared memory -> 16-byte global stores where 4 consecutive lanes cover
+//              64 contiguous bytes of one row (or the final epilogue: raw fp32 + add-mean / clip / round).
+//   (warps 6-7 idle: they keep the epilogue sets aligned on warpgroups / TMEM lane quarters)
 // The smem ring has 2-4 stages depending on the tile width (A 32 KB + B 2*bn*128 B per stage).
 #include "kernels_common.cuh"
 
@@ -34,9 +35,9 @@ namespace {
 constexpr int MAX_STAGES = 4;
 constexpr int A_PLANE = TC_BM * 128;                 // 16 KB
 constexpr int RING_BYTES = 2 * (2 * A_PLANE + 2 * TC_BN * 128);   // 192 KB: 2 stages at bn = 256, 3 at 128, 4 at <= 64
-constexpr int STAGING_BYTES = 4 * 8192;              // per epilogue warp: 32 rows x 128 B, hi and lo
+constexpr int STAGING_BYTES = 8 * 4096;              // per epilogue warp: 32 rows x 64 B, hi and lo
 constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 512;
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,13 +71,19 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// K-major SWIZZLE_128B descriptor = {lo: start address >> 4 | LBO 1 << 16, hi: SBO (1024 >> 4) | version 1 << 14 | SWIZZLE_128B 2 << 29}
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -110,11 +117,50 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-// element offset of output row m (pixel (b, oy, ox) of this launch's phase) in the NHWC output
-__device__ __forceinline__ int64_t out_row_offset(const GemmGeom& g, int m) {
-    const int b = m / g.P, p = m - b * g.P;
-    const int oy = p / g.OW, ox = p - oy * g.OW;
-    return (int64_t)b * g.out_sample_stride + ((int64_t)(oy * g.osy + g.ooy) * g.OWf + (ox * g.osx + g.oox)) * g.N;
+// Row index m -> (sample b, oy, ox) of this launch's output positions, advanced by a constant step without
+// divisions: one unsigned division pair when a tile starts, then adds and compares (step <= P, so at most
+// one wrap per level).  FC layers (P == 1) have b = m.
+struct RowIter {
+    unsigned b, oy, ox;
+};
+struct RowStep {
+    unsigned P, OW, OH, sdiv, smod, step;
+};
+__device__ __forceinline__ RowStep make_row_step(const GemmGeom& g, unsigned step) {
+    RowStep r;
+    r.P = (unsigned)g.P;
+    r.OW = (unsigned)g.OW;
+    r.OH = r.P / r.OW;
+    r.sdiv = step / r.OW;
+    r.smod = step - r.sdiv * r.OW;
+    r.step = step;
+    return r;
+}
+__device__ __forceinline__ RowIter row_init(const RowStep& rs, unsigned m) {
+    RowIter it;
+    if (rs.P == 1u) {
+        it.b = m; it.oy = 0; it.ox = 0;
+    } else {
+        it.b = m / rs.P;
+        const unsigned p = m - it.b * rs.P;
+        it.oy = p / rs.OW;
+        it.ox = p - it.oy * rs.OW;
+    }
+    return it;
+}
+__device__ __forceinline__ void row_advance(const RowStep& rs, RowIter& it) {
+    if (rs.P == 1u) {
+        it.b += rs.step;
+    } else {
+        it.ox += rs.smod;
+        it.oy += rs.sdiv;
+        if (it.ox >= rs.OW) { it.ox -= rs.OW; it.oy += 1; }
+        if (it.oy >= rs.OH) { it.oy -= rs.OH; it.b += 1; }
+    }
+}
+__device__ __forceinline__ int64_t out_offset(const GemmGeom& g, const RowIter& it) {
+    return (int64_t)it.b * g.out_sample_stride +
+           ((int64_t)((int)it.oy * g.osy + g.ooy) * g.OWf + ((int)it.ox * g.osx + g.oox)) * g.N;
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
@@ -172,6 +218,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
         const uint32_t sw = (uint32_t)((c ^ (rgrp & 7)) << 4);
         const __nv_bfloat16* in_hi = (const __nv_bfloat16*)L.in.p0;
         const __nv_bfloat16* in_lo = (const __nv_bfloat16*)L.in.p1;
+        const RowStep rs16 = make_row_step(g, 16u);
         int s = 0;
         uint32_t ph = 0;
         int cur_mt = -1;
@@ -181,18 +228,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
             const int mt = tile / num_nt;
             if (mt != cur_mt) {
                 cur_mt = mt;
+                RowIter it = row_init(rs16, (unsigned)(mt * TC_BM + rgrp));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int m = mt * TC_BM + rgrp + 16 * i;
                     if (m < L.M) {
-                        const int b = m / g.P, p = m - b * g.P;
-                        const int oy = p / g.OW, ox = p - oy * g.OW;
-                        rbase[i] = (int64_t)b * g.in_sample_stride;
-                        rpos[i] = (oy << 16) | ox;
+                        rbase[i] = (int64_t)it.b * g.in_sample_stride;
+                        rpos[i] = (int)((it.oy << 16) | it.ox);
                     } else {
                         rbase[i] = 0;
                         rpos[i] = -1;
                     }
+                    row_advance(rs16, it);
                 }
             }
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -274,12 +321,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
                     // 16-wide K steps that hold data (the K tail of the last block is skipped, not multiplied by zero)
                     int ksteps = (g.K - kb * TC_BK + 15) >> 4;
                     if (ksteps > TC_BK / 16) ksteps = TC_BK / 16;
-                    for (int k4 = 0; k4 < ksteps; ++k4) {
-                        const uint64_t da_hi = make_desc(a_hi + k4 * 32), da_lo = make_desc(a_lo + k4 * 32);
-                        const uint64_t db_hi = make_desc(b_hi + k4 * 32), db_lo = make_desc(b_lo + k4 * 32);
-                        umma_bf16(acc, da_hi, db_hi, idesc, (kb | k4) != 0 ? 1u : 0u);
-                        umma_bf16(acc, da_hi, db_lo, idesc, 1u);
-                        umma_bf16(acc, da_lo, db_hi, idesc, 1u);
+                    const uint32_t da_hi = desc_lo(a_hi), da_lo = desc_lo(a_lo), db_hi = desc_lo(b_hi), db_lo = desc_lo(b_lo);
+#pragma unroll
+                    for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                        if (k4 < ksteps) {                      // +2 per K step: 32 bytes >> 4 inside the 128-byte swizzle row
+                            umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                            umma_bf16(acc, da_hi + 2 * k4, db_lo + 2 * k4, idesc, 1u);
+                            umma_bf16(acc, da_lo + 2 * k4, db_hi + 2 * k4, idesc, 1u);
+                        }
                     }
                     umma_commit(empty(s));
                     if (kb == num_kb - 1) umma_commit(tmem_full(ab));
@@ -288,72 +337,72 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
                 if (++s == num_stages) { s = 0; ph ^= 1u; }
             }
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue warps (6..9)
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ epilogue warps (set 0: 8..11, set 1: 12..15)
+        const int set = (warp - 8) >> 2;                     // = accumulator buffer this set drains
         const int q = warp & 3;                              // TMEM lane quarter this warp may read
-        const uint32_t stg_hi = staging + (uint32_t)(warp - 6) * 8192u;
-        const uint32_t stg_lo = stg_hi + 4096u;
-        const int cchunk = lane & 7;                         // 16-byte chunk of a row segment in the copy-out phase
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t stg_hi = staging + (uint32_t)(warp - 8) * 4096u;
+        const uint32_t stg_lo = stg_hi + 2048u;
+        const int cchunk = lane & 3;                         // 16-byte chunk of a 64-byte row segment in the copy-out phase
+        const RowStep rs8 = make_row_step(g, 8u);
+        const RowStep rs1 = make_row_step(g, 1u);
+        int j = 0;                                           // tiles this set has processed
+        for (int tile = blockIdx.x + set * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, ++j) {
             const int nt = tile % num_nt, mt = tile / num_nt;
             const int n0 = nt * TC_BN;
             int bn = g.N - n0;
             bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
-            const int ab = lt & 1;
-            const int row = q * 32 + lane;                   // accumulator row owned in the TMEM-read phase
-            const int m_own = mt * TC_BM + row;
-            // rows this lane copies out: (lane >> 3) + 4*i of the warp's 32 rows
-            int64_t obase[8];
+            const int m_own = mt * TC_BM + q * 32 + lane;     // accumulator row owned in the TMEM-read phase
+            // rows this lane copies out: (lane >> 2) + 8*i of the warp's 32 rows
+            int64_t obase[4];
+            int64_t obase_own = -1;
+            if (L.out_mode == OUT_FINAL) {
+                if (m_own < L.M) obase_own = out_offset(g, row_init(rs1, (unsigned)m_own));
+            } else {
+                RowIter it = row_init(rs8, (unsigned)(mt * TC_BM + q * 32 + (lane >> 2)));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = mt * TC_BM + q * 32 + (lane >> 3) + 4 * i;
-                obase[i] = m < L.M ? out_row_offset(g, m) : -1;
-            }
-            const int64_t obase_own = m_own < L.M ? out_row_offset(g, m_own) : -1;
-            mbar_wait(tmem_full(ab), ((uint32_t)lt >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * TC_BN);
-            // bias of a 64-column block: two coalesced loads per lane, broadcast by shuffle (prefetched one block ahead)
-            float bias0 = n0 + lane < g.N ? __ldg(L.bias + n0 + lane) : 0.f;
-            float bias1 = n0 + 32 + lane < g.N ? __ldg(L.bias + n0 + 32 + lane) : 0.f;
-            for (int c0 = 0; c0 < bn; c0 += 64) {
-                uint32_t v[64];
-                tmem_ld32(taddr + c0, v);
-                tmem_ld32(taddr + c0 + 32, v + 32);
-                const int nbase = n0 + c0;
-                const float b_lo32 = bias0, b_hi32 = bias1;
-                if (c0 + 64 < bn) {
-                    bias0 = nbase + 64 + lane < g.N ? __ldg(L.bias + nbase + 64 + lane) : 0.f;
-                    bias1 = nbase + 96 + lane < g.N ? __ldg(L.bias + nbase + 96 + lane) : 0.f;
+                for (int i = 0; i < 4; ++i) {
+                    const int m = mt * TC_BM + q * 32 + (lane >> 2) + 8 * i;
+                    obase[i] = m < L.M ? out_offset(g, it) : -1;
+                    row_advance(rs8, it);
                 }
+            }
+            // bias of the first 32-column block: one coalesced load per lane, broadcast by shuffle
+            float bias_next = n0 + lane < g.N ? __ldg(L.bias + n0 + lane) : 0.f;
+            mbar_wait(tmem_full(set), (uint32_t)j & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * TC_BN);
+            for (int c0 = 0; c0 < bn; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c0, v);
+                const int nbase = n0 + c0;
+                const float bias_cur = bias_next;
+                if (c0 + 32 < bn) bias_next = nbase + 32 + lane < g.N ? __ldg(L.bias + nbase + 32 + lane) : 0.f;
                 tmem_ld_wait();
                 int nvalid = g.N - nbase;                    // multiple of 16 by construction
-                if (nvalid > 64) nvalid = 64;
+                if (nvalid > 32) nvalid = 32;
                 if (L.debug_flags & 4) continue;
                 if (L.out_mode == OUT_FINAL) {
 #pragma unroll
-                    for (int j = 0; j < 64; ++j) {
-                        const float bj = __shfl_sync(0xffffffffu, j < 32 ? b_lo32 : b_hi32, j & 31);
-                        if (j < nvalid && obase_own >= 0) {
-                            float f = __uint_as_float(v[j]) + bj;
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const float bj = __shfl_sync(0xffffffffu, bias_cur, jj);
+                        if (jj < nvalid && obase_own >= 0) {
+                            float f = __uint_as_float(v[jj]) + bj;
                             if (g.leaky) f = leaky_relu(f);
-                            final_store(L.fin, obase_own + nbase + j, f);
+                            final_store(L.fin, obase_own + nbase + jj, f);
                         }
                     }
                     continue;
                 }
-                // bias, LeakyReLU, split, swizzled staging (chunk c of row r at position c ^ (r & 7))
+                // bias, LeakyReLU, split, swizzled staging (chunk c of row r at position c ^ ((r >> 1) & 3))
 #pragma unroll
-                for (int ch = 0; ch < 8; ++ch) {
+                for (int ch = 0; ch < 4; ++ch) {
                     uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int col = ch * 8 + 2 * j;
-                        const float bj0 = __shfl_sync(0xffffffffu, col < 32 ? b_lo32 : b_hi32, col & 31);
-                        const float bj1 = __shfl_sync(0xffffffffu, col < 32 ? b_lo32 : b_hi32, (col + 1) & 31);
-                        float f0 = __uint_as_float(v[col]) + bj0;
-                        float f1 = __uint_as_float(v[col + 1]) + bj1;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int col = ch * 8 + 2 * jj;
+                        float f0 = __uint_as_float(v[col]) + __shfl_sync(0xffffffffu, bias_cur, col);
+                        float f1 = __uint_as_float(v[col + 1]) + __shfl_sync(0xffffffffu, bias_cur, col + 1);
                         if (g.leaky) {
                             f0 = leaky_relu(f0);
                             f1 = leaky_relu(f1);
@@ -361,21 +410,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
                         __nv_bfloat16 h0, l0, h1, l1;
                         split_bf16(f0, h0, l0);
                         split_bf16(f1, h1, l1);
-                        hi[j] = pack_bf16(h0, h1);
-                        lo[j] = pack_bf16(l0, l1);
+                        hi[jj] = pack_bf16(h0, h1);
+                        lo[jj] = pack_bf16(l0, l1);
                     }
-                    const uint32_t off = (uint32_t)lane * 128u + (uint32_t)((ch ^ (lane & 7)) << 4);
+                    const uint32_t off = (uint32_t)lane * 64u + (uint32_t)((ch ^ ((lane >> 1) & 3)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
                 }
                 __syncwarp();
-                // copy out: 8 consecutive lanes write the 128 contiguous bytes of one row segment
+                // copy out: 4 consecutive lanes write the 64 contiguous bytes of one row segment
                 if (cchunk * 8 < nvalid) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         if (obase[i] < 0) continue;
-                        const int r = (lane >> 3) + 4 * i;
-                        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((cchunk ^ (r & 7)) << 4);
+                        const int r = (lane >> 2) + 8 * i;
+                        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((cchunk ^ ((r >> 1) & 3)) << 4);
                         uint4 h, l;
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(stg_hi + off));
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(stg_lo + off));
@@ -389,7 +438,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
             // this warp's TMEM reads of the tile are done: hand the accumulator back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty(ab));
+            if (lane == 0) mbar_arrive(tmem_empty(set));
         }
     }
 

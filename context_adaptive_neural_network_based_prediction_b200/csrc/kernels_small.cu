@@ -200,6 +200,99 @@ int launch_conv0(const Conv0Launch& L, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// im2col for the first convolution (1 input channel): thread = (output pixel, group of 8 taps).  The
+// convolution itself then runs on the tensor cores as a GEMM with K = KP (reference pnn/tfutils.py:134-139).
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) im2col_kernel(Im2colLaunch L) {
+    const int P = L.OH * L.OW;
+    const int groups = L.KP >> 3;                       // 8 taps per thread
+    const int ppb = 256 / groups;                       // pixels per block
+    const int tiles = (P + ppb - 1) / ppb;
+    const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
+    const int pix = tile * ppb + threadIdx.x / groups;
+    const int grp = threadIdx.x % groups;
+    if (pix >= P) return;
+    const int oy = pix / L.OW, ox = pix - oy * L.OW;
+    const float* in = L.in + (int64_t)b * L.IH * L.IW;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = grp * 8 + j;
+        const int ky = t / L.k, kx = t - ky * L.k;
+        const int iy = oy * L.stride + ky - L.pad, ix = ox * L.stride + kx - L.pad;
+        v[j] = (t < L.k * L.k && iy >= 0 && iy < L.IH && ix >= 0 && ix < L.IW) ? __ldg(in + iy * L.IW + ix) : 0.f;
+    }
+    const int64_t o = ((int64_t)b * P + pix) * L.KP + grp * 8;
+    if (SPLIT) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * j], h0, l0);
+            split_bf16(v[2 * j + 1], h1, l1);
+            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        *(uint4*)((__nv_bfloat16*)L.out.p0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *(uint4*)((__nv_bfloat16*)L.out.p1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+        float4* po = (float4*)((float*)L.out.p0 + o);
+        po[0] = make_float4(v[0], v[1], v[2], v[3]);
+        po[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+int launch_im2col(const Im2colLaunch& L, cudaStream_t stream) {
+    if (L.n == 0) return 0;
+    const int P = L.OH * L.OW, ppb = 256 / (L.KP / 8);
+    const int64_t grid = (int64_t)L.n * ((P + ppb - 1) / ppb);
+    if (L.split) im2col_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(L);
+    else im2col_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// col2im of the last transposed convolution, fused with the output epilogue (reference
+// pnn/tfutils.py:455-462; TComPrediction.cpp:621-635 / tools/tools.py:49).  Gather form, fixed order
+// (ky, kx ascending): out[y, x] = bias + sum_{ky, kx : (y+pad-ky) % s == 0, ...} D[((y+pad-ky)/s, (x+pad-kx)/s), ky*k+kx].
+// ---------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(128) col2im_kernel(Col2imLaunch L) {
+    const int OH = L.IH * L.stride, OW = L.IW * L.stride, P = OH * OW;
+    const int tiles = (P + 127) >> 7;
+    const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
+    const int pix = (tile << 7) + threadIdx.x;
+    if (pix >= P) return;
+    const int y = pix / OW, x = pix - y * OW;
+    const int64_t base = (int64_t)b * L.IH * L.IW;
+    float acc = 0.f;
+    for (int ky = 0; ky < L.k; ++ky) {
+        const int ty = y + L.pad - ky;
+        if (ty < 0 || (L.stride == 2 && (ty & 1))) continue;
+        const int iy = L.stride == 2 ? ty >> 1 : ty;
+        if (iy >= L.IH) continue;
+        for (int kx = 0; kx < L.k; ++kx) {
+            const int tx = x + L.pad - kx;
+            if (tx < 0 || (L.stride == 2 && (tx & 1))) continue;
+            const int ix = L.stride == 2 ? tx >> 1 : tx;
+            if (ix >= L.IW) continue;
+            acc += act_load<SPLIT>(L.d, (base + iy * L.IW + ix) * L.NP + ky * L.k + kx);
+        }
+    }
+    final_store(L.fin, (int64_t)b * P + pix, acc + L.bias);
+}
+
+int launch_col2im(const Col2imLaunch& L, cudaStream_t stream) {
+    if (L.n == 0) return 0;
+    const int P = L.IH * L.stride * L.IW * L.stride;
+    const int64_t grid = (int64_t)L.n * ((P + 127) / 128);
+    if (L.split) col2im_kernel<true><<<(unsigned)grid, 128, 0, stream>>>(L);
+    else col2im_kernel<false><<<(unsigned)grid, 128, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Channel-wise fully-connected merger + LeakyReLU (reference pnn/tfutils.py:60-73,
 // pnn/components.py:225-231): per channel c, the 48 values of the above map (row-major) followed by
 // the 32 values of the left map are fully connected to 16 outputs.  One thread per (sample, channel),

@@ -84,7 +84,7 @@ T* upload(const std::vector<T>& v, std::vector<std::unique_ptr<DevBuf>>& keep) {
     return (T*)keep.back()->p;
 }
 
-enum StepKind { STEP_GEMM, STEP_CONV0, STEP_MERGER, STEP_TCONV_LAST };
+enum StepKind { STEP_GEMM, STEP_CONV0, STEP_MERGER, STEP_TCONV_LAST, STEP_IM2COL, STEP_COL2IM };
 
 struct Step {
     StepKind kind;
@@ -97,7 +97,7 @@ struct Step {
     const uint8_t* d_wt = nullptr;
     const float* d_bias = nullptr;
     // conv0
-    int IH = 0, IW = 0, OH = 0, OW = 0, C = 0, k = 0, stride = 0, pad = 0;
+    int IH = 0, IW = 0, OH = 0, OW = 0, C = 0, k = 0, stride = 0, pad = 0, KP = 0;
     float bias_scalar = 0.f;
 };
 
@@ -254,6 +254,19 @@ void build_fc(Net& net, const FlatFile& ff) {
     }
 }
 
+// GEMM over rows that are pixels of a [H, W] map with K contiguous values each (no taps, no stride)
+GemmGeom pixel_gemm_geom(int H, int W, int K, int N, int leaky) {
+    GemmGeom g{};
+    g.P = H * W; g.OW = W; g.Cin = K; g.TH = 1; g.TW = 1; g.IH = H; g.IW = W;
+    g.sy_o = 1; g.sy_t = 0; g.cy = 0; g.sx_o = 1; g.sx_t = 0; g.cx = 0;
+    g.in_sample_stride = (int64_t)H * W * K;
+    g.N = N; g.K = K;
+    g.OHf = H; g.OWf = W; g.osy = 1; g.ooy = 0; g.osx = 1; g.oox = 0;
+    g.out_sample_stride = (int64_t)H * W * N;
+    g.leaky = leaky;
+    return g;
+}
+
 // reference pnn/components.py:10-101, 182-261
 void build_conv(Net& net, const FlatFile& ff) {
     const int W = net.W;
@@ -278,14 +291,26 @@ void build_conv(Net& net, const FlatFile& ff) {
             net.param_count += (int64_t)wt.size() + bs.size();
             Step st;
             st.in0 = cur;
-            st.out = add_buf(net, (int64_t)oh * ow * c);
             if (i == 0) {
-                st.kind = STEP_CONV0;
-                st.IH = h; st.IW = w; st.OH = oh; st.OW = ow; st.C = c; st.k = k; st.stride = s; st.pad = pad_y;
+                // first convolution (one input channel): im2col (k*k taps padded to KP columns) + GEMM
                 if (pad_x != pad_y) throw std::runtime_error("unexpected asymmetric padding");
-                st.d_w32 = upload(wt, net.dev);          // [k*k][Cout] because Cin == 1
-                st.d_bias = upload(bs, net.dev);
+                const int KP = (k * k + 15) / 16 * 16;
+                Step im;
+                im.kind = STEP_IM2COL;
+                im.in0 = cur;
+                im.out = add_buf(net, (int64_t)oh * ow * KP);
+                im.IH = h; im.IW = w; im.OH = oh; im.OW = ow; im.k = k; im.stride = s; im.pad = pad_y; im.KP = KP;
+                net.steps.push_back(im);
+                st.kind = STEP_GEMM;
+                st.in0 = im.out;
+                st.out = add_buf(net, (int64_t)oh * ow * c);
+                st.g = pixel_gemm_geom(oh, ow, KP, c, 1);
+                std::vector<float> wkn((size_t)KP * c, 0.f);
+                for (int t = 0; t < k * k; ++t)
+                    for (int co = 0; co < c; ++co) wkn[(size_t)t * c + co] = wt[(size_t)t * c + co];   // [k,k,1,Cout]
+                add_gemm_weights(net, st, wkn, bs);
             } else {
+                st.out = add_buf(net, (int64_t)oh * ow * c);
                 st.kind = STEP_GEMM;
                 GemmGeom& g = st.g;
                 g.P = oh * ow; g.OW = ow; g.Cin = c_in; g.TH = k; g.TW = k; g.IH = h; g.IW = w;
@@ -345,12 +370,24 @@ void build_conv(Net& net, const FlatFile& ff) {
         const std::vector<float>& bs = need(ff, p + "biases", {c_out});
         net.param_count += (int64_t)wt.size() + bs.size();
         if (last) {
+            // last transposed convolution (one output channel, linear): GEMM of every input pixel with the
+            // k*k taps (D[(b,iy,ix), tap] = in[b,iy,ix,:] . w[tap,:]) + col2im with the fused output epilogue
+            const int NP = (k * k + 15) / 16 * 16;
+            Step gm;
+            gm.kind = STEP_GEMM;
+            gm.in0 = cur;
+            gm.out = add_buf(net, (int64_t)h * w * NP);
+            gm.g = pixel_gemm_geom(h, w, c, NP, 0);
+            std::vector<float> wkn((size_t)c * NP, 0.f), zero_bias((size_t)NP, 0.f);
+            for (int t = 0; t < k * k; ++t)
+                for (int ci = 0; ci < c; ++ci) wkn[(size_t)ci * NP + t] = wt[(size_t)t * c + ci];   // [k,k,1,Cin]
+            add_gemm_weights(net, gm, wkn, zero_bias);
+            net.steps.push_back(gm);
             Step st;
-            st.kind = STEP_TCONV_LAST;
-            st.in0 = cur;
+            st.kind = STEP_COL2IM;
+            st.in0 = gm.out;
             st.is_final = true;
-            st.IH = h; st.IW = w; st.C = c; st.k = k; st.stride = s; st.pad = pad;
-            st.d_w32 = upload(wt, net.dev);              // [k*k][1][Cin]
+            st.IH = h; st.IW = w; st.C = c; st.k = k; st.stride = s; st.pad = pad; st.KP = NP;
             st.bias_scalar = bs[0];
             net.steps.push_back(st);
         } else {
@@ -554,6 +591,27 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.n = (int)n; L.C = st.C; L.split = split;
                 ProfScope ps(h, stream, "merger", n * st.C, 16, 80, false);
                 h->launches += launch_merger(L, stream);
+                break;
+            }
+            case STEP_IM2COL: {
+                Im2colLaunch L{};
+                L.in = (const float*)net.ws0[st.in0]->p;
+                L.out = act_of(net, st.out);
+                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.OH = st.OH; L.OW = st.OW; L.k = st.k; L.stride = st.stride;
+                L.pad = st.pad; L.KP = st.KP; L.split = split;
+                ProfScope ps(h, stream, "im2col", n * st.OH * st.OW, st.KP, 1, false);
+                h->launches += launch_im2col(L, stream);
+                break;
+            }
+            case STEP_COL2IM: {
+                Col2imLaunch L{};
+                L.d = act_of(net, st.in0);
+                L.bias = st.bias_scalar;
+                L.fin = fin;
+                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.k = st.k; L.stride = st.stride; L.pad = st.pad; L.NP = st.KP;
+                L.split = split;
+                ProfScope ps(h, stream, "col2im", n * st.IH * st.stride * st.IW * st.stride, 1, 9, false);
+                h->launches += launch_col2im(L, stream);
                 break;
             }
             case STEP_TCONV_LAST: {

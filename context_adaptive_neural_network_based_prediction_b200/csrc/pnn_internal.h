@@ -108,6 +108,25 @@ struct Conv0Launch {
 };
 int launch_conv0(const Conv0Launch& L, cudaStream_t stream);
 
+// im2col of a one-channel context portion for the first convolution: row (b, oy, ox) gets the k*k taps
+// (zero outside the map, SAME padding) followed by zeros up to KP columns.
+struct Im2colLaunch {
+    const float* in;     // [n, IH, IW] fp32
+    Act out;             // [n*OH*OW, KP]
+    int n, IH, IW, OH, OW, k, stride, pad, KP, split;
+};
+int launch_im2col(const Im2colLaunch& L, cudaStream_t stream);
+
+// col2im of the last transposed convolution + the output epilogue: D[(b, iy, ix), ky*k+kx] holds the
+// per-tap dot products (GEMM output); out[y, x] = bias + sum over the taps with iy*s + ky - pad == y.
+struct Col2imLaunch {
+    Act d;               // [n*IH*IW, NP]
+    float bias;
+    FinalOut fin;
+    int n, IH, IW, k, stride, pad, NP, split;
+};
+int launch_col2im(const Col2imLaunch& L, cudaStream_t stream);
+
 // Channel-wise fully-connected merger (reference pnn/tfutils.py:8-73) + LeakyReLU.
 struct MergerLaunch {
     Act in0, in1;        // [n, 48, C], [n, 32, C]
