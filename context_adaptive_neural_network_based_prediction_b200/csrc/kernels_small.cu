@@ -298,53 +298,144 @@ int launch_col2im(const Col2imLaunch& L, cudaStream_t stream) {
 // the 32 values of the left map are fully connected to 16 outputs.  One thread per (sample, channel),
 // channel fastest; the weights were transposed on the host to [80][16][C] so that loads coalesce.
 // ---------------------------------------------------------------------------------------------
-// v2: thread = (channel, 4 consecutive samples): every weight load feeds 4 FMAs.
+// v4: persistent CTAs, each owns a group of 16 channels whose 80x16 weights stay in shared memory
+// ([q][channel][16 outputs + 4 pad floats]) and loops over tiles of 128 samples.  Thread = (8 channels, one
+// sample): the 8 channel values of an input pixel arrive with one 16-byte load per plane (several q in flight,
+// the kernel is otherwise bound by load latency), the weights with warp-broadcast LDS.128 (a warp works on a
+// single channel octet), and the 8 x 16 accumulators live in registers.  Fixed order: q ascending.
+constexpr int MG_CH = 16, MG_ROW = 20, MG_TILE = 128, MG_UNROLL = 4;
+constexpr int MG_SMEM = (80 * MG_CH * MG_ROW + 16 * MG_CH) * (int)sizeof(float);
+
 template <bool SPLIT>
-__global__ void __launch_bounds__(128) merger_kernel(MergerLaunch L) {
-    constexpr int SPT = 4;
-    const int cblocks = (L.C + 127) >> 7;
-    const int sgrp = blockIdx.x / cblocks, cb = blockIdx.x - sgrp * cblocks;
-    const int c = (cb << 7) + threadIdx.x;
-    if (c >= L.C) return;
-    const int b0 = sgrp * SPT;
-    float acc[SPT][16];
-#pragma unroll
-    for (int s = 0; s < SPT; ++s)
-#pragma unroll
-        for (int p = 0; p < 16; ++p) acc[s][p] = 0.f;
-    for (int q = 0; q < 80; ++q) {
-        float x[SPT];
-#pragma unroll
-        for (int s = 0; s < SPT; ++s) {
-            const int64_t b = b0 + s;
-            x[s] = b < L.n ? (q < 48 ? act_load<SPLIT>(L.in0, (b * 48 + q) * L.C + c)
-                                      : act_load<SPLIT>(L.in1, (b * 32 + (q - 48)) * L.C + c))
-                           : 0.f;
-        }
-        const float* w = L.w + q * 16 * L.C + c;
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            const float wv = __ldg(w + p * L.C);
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) acc[s][p] = fmaf(x[s], wv, acc[s][p]);
-        }
+__device__ __forceinline__ void merger_load8(const Act& a, int64_t idx, uint4& h, uint4& l) {
+    if (SPLIT) {
+        h = __ldg((const uint4*)((const __nv_bfloat16*)a.p0 + idx));
+        l = __ldg((const uint4*)((const __nv_bfloat16*)a.p1 + idx));
+    } else {
+        h = __ldg((const uint4*)((const float*)a.p0 + idx));
+        l = __ldg((const uint4*)((const float*)a.p0 + idx + 4));
     }
+}
+template <bool SPLIT>
+__device__ __forceinline__ void merger_unpack8(const uint4& h, const uint4& l, float (&x)[8]) {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    if (SPLIT) {
 #pragma unroll
-    for (int s = 0; s < SPT; ++s) {
-        const int64_t b = b0 + s;
-        if (b >= L.n) break;
+        for (int j = 0; j < 4; ++j) {
+            x[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+            x[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+        }
+    } else {
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            act_store<SPLIT>(L.out, (b * 16 + p) * L.C + c, leaky_relu(acc[s][p] + __ldg(L.bias + p * L.C + c)));
+        for (int j = 0; j < 4; ++j) {
+            x[j] = __uint_as_float(hw[j]);
+            x[4 + j] = __uint_as_float(lw[j]);
         }
     }
 }
 
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 1) merger_kernel(MergerLaunch L, int groups_per_cg) {
+    extern __shared__ float mg_s[];
+    float* w_s = mg_s;                                  // [80][16 ch][20]
+    float* b_s = mg_s + 80 * MG_CH * MG_ROW;            // [16 ch][16]
+    const int ncg = L.C / MG_CH;
+    const int cg = blockIdx.x % ncg, grp = blockIdx.x / ncg;
+    for (int i = threadIdx.x; i < 80 * 16 * MG_CH; i += 256) {
+        const int ch = i % MG_CH, qp = i / MG_CH;       // L.w is [80][16][C]: coalesced over the channel
+        const int q = qp >> 4, p = qp & 15;
+        w_s[(q * MG_CH + ch) * MG_ROW + p] = L.w[(int64_t)qp * L.C + cg * MG_CH + ch];
+    }
+    for (int i = threadIdx.x; i < 16 * MG_CH; i += 256) {
+        const int ch = i % MG_CH, p = i / MG_CH;
+        b_s[ch * 16 + p] = L.bias[p * L.C + cg * MG_CH + ch];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int oct = warp & 1;                           // channel octet of the group: warp-uniform
+    const int c0 = cg * MG_CH + oct * 8;
+    const int tiles = (L.n + MG_TILE - 1) / MG_TILE;
+    for (int tile = grp; tile < tiles; tile += groups_per_cg) {
+        const int64_t b = (int64_t)tile * MG_TILE + (warp >> 1) * 32 + lane;
+        const bool ok = b < L.n;
+        const int64_t bb = ok ? b : 0;
+        float acc[8][16];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+#pragma unroll
+            for (int p = 0; p < 16; ++p) acc[ch][p] = 0.f;
+        for (int q0 = 0; q0 < 80; q0 += MG_UNROLL) {     // 48 and 80 are multiples of MG_UNROLL
+            uint4 h[MG_UNROLL], l[MG_UNROLL];
+#pragma unroll
+            for (int u = 0; u < MG_UNROLL; ++u) {
+                const int q = q0 + u;
+                if (q < 48) merger_load8<SPLIT>(L.in0, (bb * 48 + q) * L.C + c0, h[u], l[u]);
+                else merger_load8<SPLIT>(L.in1, (bb * 32 + (q - 48)) * L.C + c0, h[u], l[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < MG_UNROLL; ++u) {
+                float x[8];
+                merger_unpack8<SPLIT>(h[u], l[u], x);
+                const float* wq = w_s + ((q0 + u) * MG_CH + oct * 8) * MG_ROW;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
+                    const float4* wr = (const float4*)(wq + ch * MG_ROW);
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float4 w4 = wr[v];
+                        acc[ch][4 * v + 0] = fmaf(x[ch], w4.x, acc[ch][4 * v + 0]);
+                        acc[ch][4 * v + 1] = fmaf(x[ch], w4.y, acc[ch][4 * v + 1]);
+                        acc[ch][4 * v + 2] = fmaf(x[ch], w4.z, acc[ch][4 * v + 2]);
+                        acc[ch][4 * v + 3] = fmaf(x[ch], w4.w, acc[ch][4 * v + 3]);
+                    }
+                }
+            }
+        }
+        if (!ok) continue;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            float y[8];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) y[ch] = leaky_relu(acc[ch][p] + b_s[(oct * 8 + ch) * 16 + p]);
+            const int64_t o = (b * 16 + p) * L.C + c0;
+            if (SPLIT) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(y[2 * j], h0, l0);
+                    split_bf16(y[2 * j + 1], h1, l1);
+                    hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                *(uint4*)((__nv_bfloat16*)L.out.p0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *(uint4*)((__nv_bfloat16*)L.out.p1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            } else {
+                float4* po = (float4*)((float*)L.out.p0 + o);
+                po[0] = make_float4(y[0], y[1], y[2], y[3]);
+                po[1] = make_float4(y[4], y[5], y[6], y[7]);
+            }
+        }
+    }
+}
+
+static int g_merger_init = 0;
+
 int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
     if (L.n == 0) return 0;
-    const int64_t grid = (int64_t)((L.n + 3) / 4) * ((L.C + 127) / 128);
-    if (L.split) merger_kernel<true><<<(unsigned)grid, 128, 0, stream>>>(L);
-    else merger_kernel<false><<<(unsigned)grid, 128, 0, stream>>>(L);
+    if (L.C % MG_CH) return -1;
+    if (!g_merger_init) {
+        cudaFuncSetAttribute(merger_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+        cudaFuncSetAttribute(merger_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+        g_merger_init = 1;
+    }
+    const int ncg = L.C / MG_CH;
+    const int tiles = (L.n + MG_TILE - 1) / MG_TILE;
+    int groups = (148 + ncg - 1) / ncg;                 // about one resident CTA per SM
+    if (groups > tiles) groups = tiles;
+    if (groups < 1) groups = 1;
+    if (L.split) merger_kernel<true><<<ncg * groups, 256, MG_SMEM, stream>>>(L, groups);
+    else merger_kernel<false><<<ncg * groups, 256, MG_SMEM, stream>>>(L, groups);
     return 1;
 }
 
