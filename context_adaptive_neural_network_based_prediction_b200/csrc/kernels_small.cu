@@ -63,25 +63,31 @@ int launch_gather_image(const GatherLaunch& L, cudaStream_t stream) {
 //   left rows [0, left_rows_valid)   copied; the reference writer only advances on available units
 //                                    (:189-205), so the copied rows are the first n_avail*unit_h ones.
 // ---------------------------------------------------------------------------------------------
+// value of element e of the flattened (above, left) context of width W, staged as described in pnn_internal.h
+__device__ __forceinline__ float hm_context_value(const int32_t* __restrict__ staged, int W, float mean, int e) {
+    const int na = 3 * W * W;
+    float v = (float)staged[HM_HEADER_INTS + e] - mean;
+    if (e < na) {
+        const int cc = e % (3 * W);
+        if (cc >= W) {
+            const int u = (cc - W) / staged[2];
+            const uint32_t bit = u < 32 ? ((uint32_t)staged[0] >> u) & 1u : ((uint32_t)staged[1] >> (u - 32)) & 1u;
+            if (!bit) v = 0.f;
+        }
+    } else if ((e - na) / W >= staged[3]) {
+        v = 0.f;
+    }
+    return v;
+}
+
 template <bool SPLIT>
 __global__ void gather_hm_kernel(GatherHmLaunch L) {
     const int W = L.W;
     const int na = 3 * W * W, total = 5 * W * W;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        float v = (float)L.staged[e] - L.mean;
-        if (e < na) {
-            const int cc = e % (3 * W);
-            if (cc >= W) {
-                const int u = (cc - W) / L.unit_w;
-                const uint32_t bit = u < 32 ? (L.above_mask_lo >> u) & 1u : (L.above_mask_hi >> (u - 32)) & 1u;
-                if (!bit) v = 0.f;
-            }
-            act_store<SPLIT>(L.above, e, v);
-        } else {
-            const int e2 = e - na;
-            if (e2 / W >= L.left_rows_valid) v = 0.f;
-            act_store<SPLIT>(L.left, e2, v);
-        }
+        const float v = hm_context_value(L.staged, W, L.mean, e);
+        if (e < na) act_store<SPLIT>(L.above, e, v);
+        else act_store<SPLIT>(L.left, e - na, v);
     }
 }
 
@@ -90,6 +96,98 @@ int launch_gather_hm(const GatherHmLaunch& L, cudaStream_t stream) {
     const int grid = (total + 255) / 256;
     if (L.split) gather_hm_kernel<true><<<grid, 256, 0, stream>>>(L);
     else gather_hm_kernel<false><<<grid, 256, 0, stream>>>(L);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batch-1 fully-connected layer for the in-loop calls (reference TComPrediction.cpp(substitution):566-584
+// runs the FC graphs with a batch of one).  Weight streaming: CTA = 16 output columns x 64 slices of K,
+// every thread reads its <= 19 float4 weights with independent loads (the layer is bound by the latency and
+// bandwidth of reading K*N*4 bytes once), the 64 partial sums of a column are added in slice order by one
+// thread: the result does not depend on the launch configuration of anything else, so encoder and decoder
+// reconstructions match bit for bit.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemv_fp32_kernel(GemvLaunch L) {
+    // CTA = 16 output columns (4 threads x float4) x 64 slices of K; N % 16 == 0
+    __shared__ float xs[1280];
+    __shared__ float red[64][17];
+    for (int k = threadIdx.x; k < L.K; k += 256) xs[k] = L.first ? hm_context_value(L.staged, L.W, L.mean, k) : L.x[k];
+    __syncthreads();
+    const int cq = threadIdx.x & 3, ks = threadIdx.x >> 2;
+    const int n = blockIdx.x * 16 + cq * 4;
+    const int kper = (L.K + 63) >> 6;
+    const int k0 = ks * kper;
+    int k1 = k0 + kper;
+    if (k1 > L.K) k1 = L.K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = L.w + (int64_t)k0 * L.N + n;
+    int k = k0;
+    for (; k + 8 <= k1; k += 8, w += 8 * L.N) {
+        float4 wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = __ldg((const float4*)(w + j * L.N));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x = xs[k + j];
+            acc[0] = fmaf(x, wv[j].x, acc[0]);
+            acc[1] = fmaf(x, wv[j].y, acc[1]);
+            acc[2] = fmaf(x, wv[j].z, acc[2]);
+            acc[3] = fmaf(x, wv[j].w, acc[3]);
+        }
+    }
+    for (; k < k1; ++k, w += L.N) {
+        const float4 wv = __ldg((const float4*)w);
+        const float x = xs[k];
+        acc[0] = fmaf(x, wv.x, acc[0]);
+        acc[1] = fmaf(x, wv.y, acc[1]);
+        acc[2] = fmaf(x, wv.z, acc[2]);
+        acc[3] = fmaf(x, wv.w, acc[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[ks][cq * 4 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int nn = blockIdx.x * 16 + threadIdx.x;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s += red[j][threadIdx.x];     // fixed order: slice 0 .. 63
+        s += L.bias[nn];
+        if (L.leaky) s = leaky_relu(s);
+        L.y[nn] = s;
+    }
+}
+
+// Last FC layer (N = W*W <= 64 outputs): one warp per output, weights transposed to [N][K] on the host so
+// that a warp streams contiguous rows with 16-byte loads; lane partials are combined by a fixed shuffle tree.
+__global__ void __launch_bounds__(128) gemv_last_kernel(GemvLaunch L) {
+    __shared__ __align__(16) float xs[1280];
+    for (int k = threadIdx.x; k < L.K; k += 128) xs[k] = L.x[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 4 + warp;
+    if (n >= L.N) return;
+    const float4* w = (const float4*)(L.w + (int64_t)n * L.K);
+    const float4* x4 = (const float4*)xs;
+    float acc = 0.f;
+    for (int i = lane; i < (L.K >> 2); i += 32) {                  // K % 4 == 0
+        const float4 wv = __ldg(w + i), xv = x4[i];
+        acc = fmaf(xv.x, wv.x, acc);
+        acc = fmaf(xv.y, wv.y, acc);
+        acc = fmaf(xv.z, wv.z, acc);
+        acc = fmaf(xv.w, wv.w, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        float s = acc + L.bias[n];
+        if (L.leaky) s = leaky_relu(s);
+        final_store(L.fin, n, s);
+    }
+}
+
+int launch_gemv(const GemvLaunch& L, cudaStream_t stream) {
+    if (L.last) gemv_last_kernel<<<(L.N + 3) / 4, 128, 0, stream>>>(L);
+    else gemv_fp32_kernel<<<L.N / 16, 256, 0, stream>>>(L);
     return 1;
 }
 
@@ -420,6 +518,12 @@ __global__ void __launch_bounds__(256, 1) merger_kernel(MergerLaunch L, int grou
 }
 
 static int g_merger_init = 0;
+
+void small_kernels_init() {
+    cudaFuncSetAttribute(merger_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+    cudaFuncSetAttribute(merger_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
+    g_merger_init = 1;
+}
 
 int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
     if (L.n == 0) return 0;

@@ -94,6 +94,7 @@ struct Step {
     // GEMM
     GemmGeom g{};
     const float* d_w32 = nullptr;
+    const float* d_w32_t = nullptr;     // [N][K] copy (final FC layer, batch-1 path)
     const uint8_t* d_wt = nullptr;
     const float* d_bias = nullptr;
     // conv0
@@ -114,6 +115,16 @@ struct Net {
     int64_t cap = 0;
     std::vector<std::unique_ptr<DevBuf>> ws0, ws1;
     DevBuf out_raw, out_u8, out_i32, out_psnr;
+    // in-loop (batch-1) path: captured launch sequence and the GEMV vectors of the FC nets
+    cudaGraphExec_t hm_exec = nullptr;
+    int hm_exec_precision = -1;
+    int hm_launches = 0;
+    DevBuf hm_vec[3];
+    void drop_hm_graph() {
+        if (hm_exec) cudaGraphExecDestroy(hm_exec);
+        hm_exec = nullptr;
+    }
+    ~Net() { drop_hm_graph(); }
 };
 
 struct FlatFile {
@@ -246,6 +257,11 @@ void build_fc(Net& net, const FlatFile& ff) {
         st.in0 = cur;
         if (i == 3) {
             st.is_final = true;
+            const std::vector<float>& w = need(ff, "fully_connected/weights_" + sfx, {dims[i], dims[i + 1]});
+            std::vector<float> wt((size_t)dims[i] * dims[i + 1]);
+            for (int k = 0; k < dims[i]; ++k)
+                for (int n = 0; n < dims[i + 1]; ++n) wt[(size_t)n * dims[i] + k] = w[(size_t)k * dims[i + 1] + n];
+            st.d_w32_t = upload(wt, net.dev);
         } else {
             st.out = add_buf(net, dims[i + 1]);
             cur = st.out;
@@ -445,12 +461,11 @@ struct pnn_handle {
     // host-API staging
     DevBuf d_images, d_idx, d_rows, d_cols, d_in0, d_in1;
     // HM path
-    int32_t* hm_staged = nullptr;    // pinned, 5*64*64 ints
+    int32_t* hm_staged = nullptr;    // pinned, header + 5*64*64 ints
     int32_t* hm_out = nullptr;       // pinned, 64*64 ints
+    int32_t* d_hm_out_mapped = nullptr;      // device alias of hm_out (mapped pinned memory)
     DevBuf d_hm_staged;
     int hm_width = 0;
-    uint32_t hm_mask_lo = 0, hm_mask_hi = 0;
-    int hm_unit_w = 4, hm_left_rows = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float hm_ms = 0.f;
     // per-kernel profiling
@@ -520,6 +535,7 @@ int64_t choose_capacity(pnn_handle* h, const Net& net, int64_t n) {
 
 void ensure_workspace(Net& net, int64_t cap) {
     if (cap <= net.cap) return;
+    net.drop_hm_graph();                      // the captured launches hold the old buffer addresses
     if (net.ws0.empty()) {
         for (size_t i = 0; i < net.buf_elems.size(); ++i) {
             net.ws0.emplace_back(new DevBuf());
@@ -773,9 +789,11 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&h->ev0));
         CUDA_TRY(cudaEventCreate(&h->ev1));
-        CUDA_TRY(cudaMallocHost((void**)&h->hm_staged, 5 * 64 * 64 * sizeof(int32_t)));
-        CUDA_TRY(cudaMallocHost((void**)&h->hm_out, 64 * 64 * sizeof(int32_t)));
-        h->d_hm_staged.reserve(5 * 64 * 64 * sizeof(int32_t));
+        CUDA_TRY(cudaMallocHost((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t)));
+        CUDA_TRY(cudaHostAlloc((void**)&h->hm_out, 64 * 64 * sizeof(int32_t), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_mapped, h->hm_out, 0));
+        h->d_hm_staged.reserve((HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t));
+        small_kernels_init();
         CUDA_TRY(gemm_tc_init());
         if (paths_file && paths_file[0]) {
             // reference hevc/hm_common/c++/source_common/tools.cpp:40-110 (parse_file_strings_three_keys):
@@ -1003,8 +1021,8 @@ int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic
             throw std::runtime_error("inconsistent neighbouring unit description");
         }
         const int W = width, cw = 3 * W;
-        int32_t* above = h->hm_staged;
-        int32_t* left = h->hm_staged + 3 * W * W;
+        int32_t* above = h->hm_staged + HM_HEADER_INTS;
+        int32_t* left = above + 3 * W * W;
         const int total = above_units + left_units + 1;
         uint32_t lo = 0, hi = 0;
         int left_rows;
@@ -1021,7 +1039,7 @@ int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic
                 for (int u = above_units; u * unit_width < 2 * W; ++u) (u < 32 ? lo : hi) |= 1u << (u & 31);
             }
         } else {
-            memset(h->hm_staged, 0, 5 * W * W * sizeof(int32_t));
+            memset(above, 0, 5 * W * W * sizeof(int32_t));
             // extraction_context.cpp:119-127: the W x W block above-left is always copied
             const int32_t* p = roi_origin - (int64_t)W * pic_stride - W;
             for (int i = 0; i < W; ++i, p += pic_stride) memcpy(above + i * cw, p, W * sizeof(int32_t));
@@ -1045,15 +1063,64 @@ int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic
             for (int i = 0; i < left_rows; ++i, p += pic_stride) memcpy(left + i * W, p, W * sizeof(int32_t));
         }
         h->hm_width = W;
-        h->hm_mask_lo = lo;
-        h->hm_mask_hi = hi;
-        h->hm_unit_w = unit_width;
-        h->hm_left_rows = left_rows;
+        h->hm_staged[0] = (int32_t)lo;
+        h->hm_staged[1] = (int32_t)hi;
+        h->hm_staged[2] = unit_width;
+        h->hm_staged[3] = left_rows;
     } catch (const std::exception& e) {
         h->hm_width = 0;
         return fail(h, e);
     }
     return 0;
+}
+
+// Enqueues the launches of one in-loop prediction on `s` (called once per net under stream capture).
+static void enqueue_hm(pnn_handle* h, Net& net, cudaStream_t s) {
+    const int W = net.W;
+    const bool split = h->precision == PNN_PRECISION_BF16X3;
+    const size_t staged_bytes = (size_t)(HM_HEADER_INTS + 5 * W * W) * sizeof(int32_t);
+    CUDA_TRY(cudaMemcpyAsync(h->d_hm_staged.p, h->hm_staged, staged_bytes, cudaMemcpyHostToDevice, s));
+    FinalOut fin{};
+    // the last kernel writes the (<= 16 KB) prediction straight into mapped pinned host memory: no copy node
+    fin.i32 = h->d_hm_out_mapped;
+    fin.mean = h->mean;
+    fin.round_mode = PNN_ROUND_HALF_AWAY;
+    int launches = 0;
+    if (net.is_fc) {
+        // batch-1 FC nets: fp32 weight-streaming GEMV chain, HM gather fused into the first layer
+        int layer = 0;
+        for (const Step& st : net.steps) {
+            GemvLaunch L{};
+            L.w = st.is_final ? st.d_w32_t : st.d_w32;
+            L.bias = st.d_bias;
+            L.K = st.g.K; L.N = st.g.N; L.leaky = st.g.leaky;
+            L.first = layer == 0;
+            L.last = st.is_final;
+            L.x = layer > 0 ? (const float*)net.hm_vec[layer - 1].p : nullptr;
+            L.y = st.is_final ? nullptr : (float*)net.hm_vec[layer].p;
+            L.staged = (const int32_t*)h->d_hm_staged.p;
+            L.W = W;
+            L.mean = h->mean;
+            L.fin = fin;
+            launches += launch_gemv(L, s);
+            ++layer;
+        }
+    } else {
+        GatherHmLaunch G{};
+        G.staged = (const int32_t*)h->d_hm_staged.p;
+        G.W = W;
+        G.mean = h->mean;
+        G.above = act_of(net, net.in_above);
+        G.left = act_of(net, net.in_left);
+        G.split = 0;
+        launches += launch_gather_hm(G, s);
+        const int64_t before = h->launches;
+        run_net(h, net, 1, fin, s);
+        launches += (int)(h->launches - before);
+        h->launches = before;
+    }
+    (void)split;
+    net.hm_launches = launches;
 }
 
 int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
@@ -1065,44 +1132,42 @@ int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
         // reference TComPrediction.cpp(substitution):564: FC nets for widths 4 and 8, convolutional above
         Net& net = *find_net(h, width, width <= 8);
         const int W = width;
-        const bool split = h->precision == PNN_PRECISION_BF16X3;
         ensure_workspace(net, 1);
         cudaStream_t s = h->stream;
-        CUDA_TRY(cudaEventRecord(h->ev0, s));
-        CUDA_TRY(cudaMemcpyAsync(h->d_hm_staged.p, h->hm_staged, 5 * W * W * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        GatherHmLaunch G{};
-        G.staged = (const int32_t*)h->d_hm_staged.p;
-        G.W = W;
-        G.above_mask_lo = h->hm_mask_lo;
-        G.above_mask_hi = h->hm_mask_hi;
-        G.unit_w = h->hm_unit_w;
-        G.left_rows_valid = h->hm_left_rows;
-        G.mean = h->mean;
-        if (net.is_fc) {
-            Act flat = act_of(net, net.in_above);
-            G.above = flat;
-            G.left = flat;
-            if (split) {
-                G.left.p0 = (__nv_bfloat16*)flat.p0 + 3 * W * W;
-                G.left.p1 = (__nv_bfloat16*)flat.p1 + 3 * W * W;
-            } else {
-                G.left.p0 = (float*)flat.p0 + 3 * W * W;
+        if (!net.hm_exec || net.hm_exec_precision != h->precision) {
+            // capture the launch sequence once; every later call replays it (the per-call availability
+            // masks travel in the staged header, so no kernel parameter changes between calls)
+            net.drop_hm_graph();
+            if (net.is_fc) {
+                for (int i = 0; i < 3; ++i) net.hm_vec[i].reserve(1280 * sizeof(float));   // no allocation under capture
             }
-            G.split = split;
-        } else {
-            G.above = act_of(net, net.in_above);
-            G.left = act_of(net, net.in_left);
-            G.split = 0;
+            const bool prof = h->profiling;
+            h->profiling = false;
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueue_hm(h, net, s);
+            } catch (...) {
+                cudaStreamEndCapture(s, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                h->profiling = prof;
+                throw;
+            }
+            h->profiling = prof;
+            CUDA_TRY(cudaStreamEndCapture(s, &graph));
+            cudaError_t e = cudaGraphInstantiate(&net.hm_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                net.hm_exec = nullptr;
+                throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            }
+            net.hm_exec_precision = h->precision;
         }
-        h->launches += launch_gather_hm(G, s);
-        FinalOut fin{};
-        fin.i32 = (int32_t*)net.out_i32.p;
-        fin.mean = h->mean;
-        fin.round_mode = PNN_ROUND_HALF_AWAY;
-        run_net(h, net, 1, fin, s);
-        CUDA_TRY(cudaMemcpyAsync(h->hm_out, net.out_i32.p, W * W * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaEventRecord(h->ev0, s));
+        CUDA_TRY(cudaGraphLaunch(net.hm_exec, s));
         CUDA_TRY(cudaEventRecord(h->ev1, s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        h->launches += net.hm_launches;
         CUDA_TRY(cudaEventElapsedTime(&h->hm_ms, h->ev0, h->ev1));
         // reference TComPrediction.cpp(substitution):626-635: row-major copy with HM's stride
         for (int i = 0; i < W; ++i) memcpy(dst + (int64_t)i * dst_stride, h->hm_out + i * W, W * sizeof(int32_t));

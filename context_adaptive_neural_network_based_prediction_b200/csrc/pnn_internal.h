@@ -164,17 +164,39 @@ struct GatherLaunch {
 int launch_gather_image(const GatherLaunch& L, cudaStream_t stream);
 
 // HM gather: staged int32 context -> masked, mean-centred (reference extraction_context.cpp:56-205).
+// The per-call availability information travels in a 4-int header in front of the pixels, so that kernel
+// parameters are identical for every call and the launch sequence can be replayed as a CUDA graph:
+//   staged[0], staged[1]  bit i: above / above-right unit i available (units of staged[2] columns)
+//   staged[2]             unit width
+//   staged[3]             rows of the left portion that are copied (the rest stays zero)
+//   staged[4 ...]         [W*3W] above rows then [2W*W] left rows, raw reconstruction pixels
+constexpr int HM_HEADER_INTS = 4;
 struct GatherHmLaunch {
-    const int32_t* staged;      // [W*3W] above rows then [2W*W] left rows, raw reconstruction pixels
+    const int32_t* staged;
     int W;
-    uint32_t above_mask_lo, above_mask_hi;  // bit i: above/above-right unit i available (units of unit_w columns)
-    int unit_w;
-    int left_rows_valid;        // rows of the left portion that are copied (rest stay zero)
     float mean;
     Act above, left;
     int split;
 };
 int launch_gather_hm(const GatherHmLaunch& L, cudaStream_t stream);
+
+// Batch-1 fully-connected layer (in-loop path): y = act(x W + b) as a weight-streaming fp32 GEMV with a
+// fixed reduction order; the first layer reads the staged HM context (gather fused), the last one runs the
+// output epilogue.
+struct GemvLaunch {
+    const float* w;          // [K][N] fp32 ([N][K] for the last layer)
+    const float* bias;
+    const float* x;          // [K] (unused by the first layer)
+    float* y;                // [N] (unused by the last layer)
+    int K, N, leaky;
+    int first, last;
+    const int32_t* staged;   // first layer: header + pixels (see GatherHmLaunch)
+    int W;
+    float mean;
+    FinalOut fin;
+};
+int launch_gemv(const GemvLaunch& L, cudaStream_t stream);
+void small_kernels_init();
 
 int launch_win_flags(const double* psnr, const double* baseline, int64_t n, uint8_t* win, cudaStream_t stream);
 
