@@ -66,6 +66,7 @@ int launch_gather_image(const GatherLaunch& L, cudaStream_t stream) {
 // value of element e of the flattened (above, left) context of width W, staged as described in pnn_internal.h
 __device__ __forceinline__ float hm_context_value(const int32_t* __restrict__ staged, int W, float mean, int e) {
     const int na = 3 * W * W;
+    if (staged[2] == 0) return __int_as_float(staged[HM_HEADER_INTS + e]);   // float mode: context already pre-processed
     float v = (float)staged[HM_HEADER_INTS + e] - mean;
     if (e < na) {
         const int cc = e % (3 * W);

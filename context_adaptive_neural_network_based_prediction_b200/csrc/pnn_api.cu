@@ -464,6 +464,8 @@ struct pnn_handle {
     int32_t* hm_staged = nullptr;    // pinned, header + 5*64*64 ints
     int32_t* hm_out = nullptr;       // pinned, 64*64 ints
     int32_t* d_hm_out_mapped = nullptr;      // device alias of hm_out (mapped pinned memory)
+    float* hm_out_raw = nullptr;             // pinned + mapped, 64*64 floats (raw prediction)
+    float* d_hm_out_raw_mapped = nullptr;
     DevBuf d_hm_staged;
     int hm_width = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -792,6 +794,8 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
         CUDA_TRY(cudaMallocHost((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t)));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_out, 64 * 64 * sizeof(int32_t), cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_mapped, h->hm_out, 0));
+        CUDA_TRY(cudaHostAlloc((void**)&h->hm_out_raw, 64 * 64 * sizeof(float), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_raw_mapped, h->hm_out_raw, 0));
         h->d_hm_staged.reserve((HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t));
         small_kernels_init();
         CUDA_TRY(gemm_tc_init());
@@ -840,6 +844,7 @@ void pnn_destroy(pnn_handle* h) {
     h->nets.clear();
     if (h->hm_staged) cudaFreeHost(h->hm_staged);
     if (h->hm_out) cudaFreeHost(h->hm_out);
+    if (h->hm_out_raw) cudaFreeHost(h->hm_out_raw);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1083,6 +1088,7 @@ static void enqueue_hm(pnn_handle* h, Net& net, cudaStream_t s) {
     FinalOut fin{};
     // the last kernel writes the (<= 16 KB) prediction straight into mapped pinned host memory: no copy node
     fin.i32 = h->d_hm_out_mapped;
+    fin.raw = h->d_hm_out_raw_mapped;
     fin.mean = h->mean;
     fin.round_mode = PNN_ROUND_HALF_AWAY;
     int launches = 0;
@@ -1123,6 +1129,47 @@ static void enqueue_hm(pnn_handle* h, Net& net, cudaStream_t s) {
     net.hm_launches = launches;
 }
 
+// Runs the staged batch-1 prediction of `net` (captures the launch sequence on first use).
+static void run_hm(pnn_handle* h, Net& net) {
+    ensure_workspace(net, 1);
+    cudaStream_t s = h->stream;
+    if (!net.hm_exec || net.hm_exec_precision != h->precision) {
+        // capture the launch sequence once; every later call replays it (the per-call availability
+        // masks travel in the staged header, so no kernel parameter changes between calls)
+        net.drop_hm_graph();
+        if (net.is_fc) {
+            for (int i = 0; i < 3; ++i) net.hm_vec[i].reserve(1280 * sizeof(float));   // no allocation under capture
+        }
+        const bool prof = h->profiling;
+        h->profiling = false;
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue_hm(h, net, s);
+        } catch (...) {
+            cudaStreamEndCapture(s, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            h->profiling = prof;
+            throw;
+        }
+        h->profiling = prof;
+        CUDA_TRY(cudaStreamEndCapture(s, &graph));
+        cudaError_t e = cudaGraphInstantiate(&net.hm_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {
+            net.hm_exec = nullptr;
+            throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+        net.hm_exec_precision = h->precision;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev0, s));
+    CUDA_TRY(cudaGraphLaunch(net.hm_exec, s));
+    CUDA_TRY(cudaEventRecord(h->ev1, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->launches += net.hm_launches;
+    CUDA_TRY(cudaEventElapsedTime(&h->hm_ms, h->ev0, h->ev1));
+}
+
 int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
     if (!h) return -1;
     try {
@@ -1132,45 +1179,38 @@ int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
         // reference TComPrediction.cpp(substitution):564: FC nets for widths 4 and 8, convolutional above
         Net& net = *find_net(h, width, width <= 8);
         const int W = width;
-        ensure_workspace(net, 1);
-        cudaStream_t s = h->stream;
-        if (!net.hm_exec || net.hm_exec_precision != h->precision) {
-            // capture the launch sequence once; every later call replays it (the per-call availability
-            // masks travel in the staged header, so no kernel parameter changes between calls)
-            net.drop_hm_graph();
-            if (net.is_fc) {
-                for (int i = 0; i < 3; ++i) net.hm_vec[i].reserve(1280 * sizeof(float));   // no allocation under capture
-            }
-            const bool prof = h->profiling;
-            h->profiling = false;
-            cudaGraph_t graph = nullptr;
-            CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            try {
-                enqueue_hm(h, net, s);
-            } catch (...) {
-                cudaStreamEndCapture(s, &graph);
-                if (graph) cudaGraphDestroy(graph);
-                h->profiling = prof;
-                throw;
-            }
-            h->profiling = prof;
-            CUDA_TRY(cudaStreamEndCapture(s, &graph));
-            cudaError_t e = cudaGraphInstantiate(&net.hm_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e != cudaSuccess) {
-                net.hm_exec = nullptr;
-                throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-            }
-            net.hm_exec_precision = h->precision;
-        }
-        CUDA_TRY(cudaEventRecord(h->ev0, s));
-        CUDA_TRY(cudaGraphLaunch(net.hm_exec, s));
-        CUDA_TRY(cudaEventRecord(h->ev1, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        h->launches += net.hm_launches;
-        CUDA_TRY(cudaEventElapsedTime(&h->hm_ms, h->ev0, h->ev1));
+        run_hm(h, net);
         // reference TComPrediction.cpp(substitution):626-635: row-major copy with HM's stride
         for (int i = 0; i < W; ++i) memcpy(dst + (int64_t)i * dst_stride, h->hm_out + i * W, W * sizeof(int32_t));
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat, const float* left, float* out) {
+    if (!h) return -1;
+    try {
+        if (!above_or_flat || !out) throw std::runtime_error("NULL buffer");
+        if (width != 4 && width != 8 && width != 16 && width != 32 && width != 64) {
+            throw std::runtime_error("the width of the TB does not belong to {4, 8, 16, 32, 64}");
+        }
+        CUDA_TRY(cudaSetDevice(h->device));
+        Net& net = *find_net(h, width, width <= 8);
+        const int W = width;
+        if (!net.is_fc && !left) throw std::runtime_error("NULL buffer");
+        h->hm_staged[0] = h->hm_staged[1] = h->hm_staged[3] = 0;
+        h->hm_staged[2] = 0;                                  // float mode (see pnn_internal.h)
+        float* px = (float*)(h->hm_staged + HM_HEADER_INTS);
+        if (net.is_fc) {
+            memcpy(px, above_or_flat, (size_t)5 * W * W * sizeof(float));
+        } else {
+            memcpy(px, above_or_flat, (size_t)3 * W * W * sizeof(float));
+            memcpy(px + 3 * W * W, left, (size_t)2 * W * W * sizeof(float));
+        }
+        h->hm_width = 0;                                       // a staged pnn_set_context is consumed
+        run_hm(h, net);
+        memcpy(out, h->hm_out_raw, (size_t)W * W * sizeof(float));
     } catch (const std::exception& e) {
         return fail(h, e);
     }

@@ -167,7 +167,7 @@ int launch_gather_image(const GatherLaunch& L, cudaStream_t stream);
 // The per-call availability information travels in a 4-int header in front of the pixels, so that kernel
 // parameters are identical for every call and the launch sequence can be replayed as a CUDA graph:
 //   staged[0], staged[1]  bit i: above / above-right unit i available (units of staged[2] columns)
-//   staged[2]             unit width
+//   staged[2]             unit width; 0 = the pixels are float bits of an already pre-processed context
 //   staged[3]             rows of the left portion that are copied (the rest stays zero)
 //   staged[4 ...]         [W*3W] above rows then [2W*W] left rows, raw reconstruction pixels
 constexpr int HM_HEADER_INTS = 4;

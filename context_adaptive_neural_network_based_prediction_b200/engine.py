@@ -183,6 +183,14 @@ class Engine(object):
         self._check(self._lib.pnn_set_context(self._h, width, ctypes.c_void_p(origin), stride, _ptr(flags),
                                               int(num_intra_neighbor), unit_width, unit_height, above_units, left_units))
 
+    def predict_hm_context(self, width, above_or_flat, left=None):
+        """Batch-1 call with an already extracted float context (what Session::Run does in the reference's HM)."""
+        a = numpy.ascontiguousarray(above_or_flat, dtype=numpy.float32)
+        l = None if left is None else numpy.ascontiguousarray(left, dtype=numpy.float32)
+        out = numpy.empty((width, width), dtype=numpy.float32)
+        self._check(self._lib.pnn_predict_hm_context(self._h, width, _ptr(a), _ptr(l), _ptr(out)))
+        return out
+
     def predict_hm(self, width, dst_stride=None):
         """NN branch of predIntraAng: returns the int32 [W, W] prediction (HM rounding)."""
         stride = width if dst_stride is None else dst_stride

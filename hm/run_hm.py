@@ -1,0 +1,74 @@
+"""BASELINE.json configs[3]: HM-16.15 substitution encoder + decoder, first-frame intra of a synthetic frame.
+
+Runs the executables built by hm/build_hm.sh (the reference's codec, unmodified, linked to libpnn_cuda through
+hm/shim/), with seeded random-init PNN weights (the pretrained HM weights are not shipped with the reference),
+and prints one JSON object per QP: wall times, HM's own "Total Time", PNN call statistics per block width,
+decoder picture-hash status and whether encoder and decoder reconstructions are byte-identical.
+"""
+import argparse, json, os, pickle, re, subprocess, sys, tempfile, time
+import numpy
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from context_adaptive_neural_network_based_prediction_b200 import weights
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--width', type=int, default=1920)
+ap.add_argument('--height', type=int, default=1080)
+ap.add_argument('--qps', default='22,27,32,37')
+ap.add_argument('--variant', default='substitution')
+ap.add_argument('--seed', type=int, default=0)
+args = ap.parse_args()
+
+build = os.path.join(ROOT, 'hm', '_build')
+enc = os.path.join(build, 'TAppEncoderStatic_' + args.variant)
+dec = os.path.join(build, 'TAppDecoderStatic_' + args.variant)
+cfg = os.path.join(build, 'intra_main_rext.cfg')
+tmp = tempfile.mkdtemp(prefix='pnn_hm_')
+# weights: FC-4, FC-8, CONV-16, CONV-32, CONV-64 (hevc/hm_common/paths_to_graphs_output/pair.txt format)
+lines = []
+for w, is_fc in ((4, True), (8, True), (16, False), (32, False), (64, False)):
+    path = os.path.join(tmp, 'net_%d.pnnw' % w)
+    weights.save_flat(path, w, is_fc, weights.init_weights(w, is_fc, seed=w))
+    lines += ['%d,0,0,%s' % (w, path), '%d,1,0,%s' % (w, path)]
+paths_file = os.path.join(tmp, 'paths.txt')
+open(paths_file, 'w').write('\n'.join(lines) + '\n')
+mean_file = os.path.join(tmp, 'mean_training.pkl')
+pickle.dump(bench.MEAN, open(mean_file, 'wb'), protocol=2)
+frame = bench.synthetic_image(args.height, args.width, args.seed)
+yuv = os.path.join(tmp, 'in.yuv')
+frame.tofile(yuv)
+extra = ['--PathToAdditionalDirectory=' + tmp, '--PathToMeanTraining=' + mean_file, '--PathToFilePathsToGraphsOutput=' + paths_file]
+
+for qp in [int(q) for q in args.qps.split(',')]:
+    bit, rec_e, rec_d = (os.path.join(tmp, n % qp) for n in ('str_%d.bin', 'rec_enc_%d.yuv', 'rec_dec_%d.yuv'))
+    stats = os.path.join(tmp, 'stats_%d.txt' % qp)
+    env = dict(os.environ, PNN_HM_STATS=stats)
+    cmd = [enc, '-c', cfg, '-i', yuv, '-b', bit, '-o', rec_e, '-wdt', str(args.width), '-hgt', str(args.height),
+           '--InputBitDepth=8', '--InputChromaFormat=400', '--FramesToBeEncoded=1', '--QP=%d' % qp] + extra
+    t0 = time.time()
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    t_enc = time.time() - t0
+    if p.returncode != 0:
+        print(json.dumps({'qp': qp, 'error': 'encoder failed', 'stderr': p.stderr[-800:], 'stdout': p.stdout[-400:]}))
+        continue
+    enc_total = re.findall(r'Total Time:\s+([0-9.]+) sec', p.stdout)
+    bits = re.findall(r'Bytes written to file:\s+(\d+)', p.stdout)
+    psnr = re.findall(r'\s+1\s+a\s+([0-9.]+)\s+([0-9.]+)', p.stdout)
+    enc_stats = open(stats).read().strip().split('\n') if os.path.exists(stats) else []
+    stats_d = os.path.join(tmp, 'stats_dec_%d.txt' % qp)
+    t0 = time.time()
+    d = subprocess.run([dec, '-b', bit, '-o', rec_d, '-d', '8'] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, PNN_HM_STATS=stats_d))
+    t_dec = time.time() - t0
+    dec_total = re.findall(r'Total Time:\s+([0-9.]+) sec', d.stdout)
+    same = os.path.exists(rec_e) and os.path.exists(rec_d) and open(rec_e, 'rb').read() == open(rec_d, 'rb').read()
+    print(json.dumps({
+        'config': 'configs[3]: HM-16.15 %s, first-frame intra, synthetic %dx%d 4:0:0, intra_main_rext.cfg' % (args.variant, args.width, args.height),
+        'qp': qp, 'encoder_wall_s': t_enc, 'encoder_total_time_s': float(enc_total[0]) if enc_total else None,
+        'decoder_wall_s': t_dec, 'decoder_total_time_s': float(dec_total[0]) if dec_total else None,
+        'bytes': int(bits[0]) if bits else None, 'y_psnr_kbps': psnr[0] if psnr else None,
+        'decoder_rc': d.returncode, 'decoder_hash_ok': '(OK)' in d.stdout and 'ERROR' not in d.stdout,
+        'recon_enc_equals_dec': same, 'pnn_encoder': enc_stats,
+        'pnn_decoder': open(stats_d).read().strip().split('\n') if os.path.exists(stats_d) else [],
+    }), flush=True)

@@ -87,6 +87,16 @@ int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic
 int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride);
 
 /*
+ * In-loop call with an already extracted context: what Session::Run does in the reference's HM
+ * (TComPrediction.cpp(substitution):572-579 / 601-608) after extract_context_portions filled the
+ * batch-1 input tensors (TComPattern.cpp:366-380).  FC nets: `above_or_flat` is [5*W*W], `left` NULL;
+ * conv nets: `above_or_flat` [W*3W], `left` [2W*W] (mean-centred, masked floats).  `out` receives the raw
+ * float32 prediction [W*W] like the output tensor of Session::Run.  Same batch-1 kernels and reduction
+ * order as pnn_predict_hm.  Synchronous.
+ */
+int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat, const float* left, float* out);
+
+/*
  * Offline path with already pre-processed contexts: pnn.batching.predict_by_batch_via_pnn
  * (pnn/batching.py:7-88).  FC nets: `above_or_flat` is [n, 5*W*W], `left` is NULL.
  * Conv nets: `above_or_flat` is [n, W, 3W, 1] and `left` is [n, 2W, W, 1].  `out` receives the raw
