@@ -1196,9 +1196,13 @@ int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat,
             throw std::runtime_error("the width of the TB does not belong to {4, 8, 16, 32, 64}");
         }
         CUDA_TRY(cudaSetDevice(h->device));
-        Net& net = *find_net(h, width, width <= 8);
+        // the net loaded for this width: fully-connected if there is one (the reference's choice for widths 4
+        // and 8, TComPrediction.cpp:564-566), else convolutional -- a convolutional net may also serve widths 4
+        // and 8, its two portions are then the two halves of the flattened context (TComPattern.cpp:352-353)
+        const bool has_fc = h->nets.count({width, 1}) != 0;
+        Net& net = *find_net(h, width, has_fc ? 1 : 0);
         const int W = width;
-        if (!net.is_fc && !left) throw std::runtime_error("NULL buffer");
+        if (!net.is_fc && !left) left = above_or_flat + 3 * W * W;
         h->hm_staged[0] = h->hm_staged[1] = h->hm_staged[3] = 0;
         h->hm_staged[2] = 0;                                  // float mode (see pnn_internal.h)
         float* px = (float*)(h->hm_staged + HM_HEADER_INTS);

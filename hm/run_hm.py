@@ -18,6 +18,9 @@ ap.add_argument('--height', type=int, default=1080)
 ap.add_argument('--qps', default='22,27,32,37')
 ap.add_argument('--variant', default='substitution')
 ap.add_argument('--seed', type=int, default=0)
+ap.add_argument('--image', default='', help='.npy uint8 luminance image instead of the synthetic frame')
+ap.add_argument('--trained-small-nets', action='store_true',
+                help='widths 4 and 8 use the two pretrained checkpoints the reference ships (CONV-4, CONV-8, tests/golden/)')
 args = ap.parse_args()
 
 build = os.path.join(ROOT, 'hm', '_build')
@@ -29,16 +32,22 @@ tmp = tempfile.mkdtemp(prefix='pnn_hm_')
 lines = []
 for w, is_fc in ((4, True), (8, True), (16, False), (32, False), (64, False)):
     path = os.path.join(tmp, 'net_%d.pnnw' % w)
-    weights.save_flat(path, w, is_fc, weights.init_weights(w, is_fc, seed=w))
+    if args.trained_small_nets and w <= 8:
+        path = os.path.join(ROOT, 'tests', 'golden', 'conv%d_single.pnnw' % w)
+    else:
+        weights.save_flat(path, w, is_fc, weights.init_weights(w, is_fc, seed=w))
     lines += ['%d,0,0,%s' % (w, path), '%d,1,0,%s' % (w, path)]
 paths_file = os.path.join(tmp, 'paths.txt')
 open(paths_file, 'w').write('\n'.join(lines) + '\n')
 mean_file = os.path.join(tmp, 'mean_training.pkl')
 pickle.dump(bench.MEAN, open(mean_file, 'wb'), protocol=2)
 frame = bench.synthetic_image(args.height, args.width, args.seed)
+if args.image:
+    frame = numpy.ascontiguousarray(numpy.load(args.image), dtype=numpy.uint8)
+    args.height, args.width = frame.shape
 yuv = os.path.join(tmp, 'in.yuv')
 frame.tofile(yuv)
-extra = ['--PathToAdditionalDirectory=' + tmp, '--PathToMeanTraining=' + mean_file, '--PathToFilePathsToGraphsOutput=' + paths_file]
+extra = [] if args.variant == 'regular' else ['--PathToAdditionalDirectory=' + tmp, '--PathToMeanTraining=' + mean_file, '--PathToFilePathsToGraphsOutput=' + paths_file]
 
 for qp in [int(q) for q in args.qps.split(',')]:
     bit, rec_e, rec_d = (os.path.join(tmp, n % qp) for n in ('str_%d.bin', 'rec_enc_%d.yuv', 'rec_dec_%d.yuv'))
@@ -64,8 +73,8 @@ for qp in [int(q) for q in args.qps.split(',')]:
     dec_total = re.findall(r'Total Time:\s+([0-9.]+) sec', d.stdout)
     same = os.path.exists(rec_e) and os.path.exists(rec_d) and open(rec_e, 'rb').read() == open(rec_d, 'rb').read()
     print(json.dumps({
-        'config': 'configs[3]: HM-16.15 %s, first-frame intra, synthetic %dx%d 4:0:0, intra_main_rext.cfg' % (args.variant, args.width, args.height),
-        'qp': qp, 'encoder_wall_s': t_enc, 'encoder_total_time_s': float(enc_total[0]) if enc_total else None,
+        'config': 'configs[3]: HM-16.15 %s, first-frame intra, %s %dx%d 4:0:0, intra_main_rext.cfg' % (args.variant, os.path.basename(args.image) if args.image else 'synthetic', args.width, args.height),
+        'trained_small_nets': args.trained_small_nets, 'qp': qp, 'encoder_wall_s': t_enc, 'encoder_total_time_s': float(enc_total[0]) if enc_total else None,
         'decoder_wall_s': t_dec, 'decoder_total_time_s': float(dec_total[0]) if dec_total else None,
         'bytes': int(bits[0]) if bits else None, 'y_psnr_kbps': psnr[0] if psnr else None,
         'decoder_rc': d.returncode, 'decoder_hash_ok': '(OK)' in d.stdout and 'ERROR' not in d.stdout,

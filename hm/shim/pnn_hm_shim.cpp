@@ -66,8 +66,9 @@ Status Session::Run(const std::vector<std::pair<string, Tensor> >& inputs, const
     if (!outputs) return Status("`outputs` is NULL");
     const float* above_or_flat(NULL);
     const float* left(NULL);
-    if (is_fc_) {
-        if (inputs.size() != 1) return Status("a fully-connected PNN takes one input");
+    if (inputs.size() == 1) {
+        // flattened context (widths 4 and 8); a convolutional net loaded for such a width reads its two
+        // portions from the two halves of the flattened context (handled by the library)
         above_or_flat = inputs[0].second.flat<float>().data();
     } else {
         if (inputs.size() != 2) return Status("a convolutional PNN takes two inputs");
