@@ -24,7 +24,7 @@ for V in $VARIANTS; do
   if [ "$V" != "regular" ]; then
     LIBSRCS="$LIBSRCS $COMMON/extraction_context.cpp $COMMON/tools.cpp $COMMON/visualization_debugging.cpp $ROOT/hm/shim/pnn_hm_shim.cpp"
   else
-    LIBSRCS="$LIBSRCS $COMMON/tools.cpp"
+    LIBSRCS="$LIBSRCS $COMMON/tools.cpp $COMMON/visualization_debugging.cpp"
   fi
   ENCSRCS=$(ls $SRC/App/TAppEncoder/*.cpp)
   DECSRCS=$(ls $SRC/App/TAppDecoder/*.cpp)

@@ -73,3 +73,53 @@ def test_hm_error_behaviour(engine, weights_dir):
     engine.set_context(8, plane, 11, 13, flags, 9)
     with pytest.raises(PnnError):
         engine.predict_hm(16)                                                   # width mismatch
+
+
+@pytest.mark.parametrize('width', [4, 8, 16, 32])
+def test_hm_context_call_matches_call_pair(engine, weights_dir, width):
+    """pnn_predict_hm_context (what Session::Run does in HM, contexts already extracted on the host) runs the same
+    batch-1 kernels as the pnn_set_context / pnn_predict_hm pair: same raw prediction, bit for bit after rounding."""
+    from oracle import context, epilogue
+    is_fc = width <= 8
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=60 + width, gain=helpers.GAIN[(width, is_fc)])
+    engine.load_net(path)
+    engine.set_precision('bf16x3')
+    plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 9).astype(numpy.int32)
+    orow, ocol = width + 2, width + 7
+    units = 2 * width // 4
+    flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+    flags[:units // 2] = 0
+    n_avail = int(flags.sum())
+    engine.set_context(width, plane, orow, ocol, flags, n_avail)
+    pair = engine.predict_hm(width)
+    stride = plane.shape[1]
+    code, above, left = context.extract_context_portions_hm(plane.ravel(), stride, orow * stride + ocol, flags, n_avail, 4, 4,
+                                                            units, units, width, MEAN)
+    raw = engine.predict_hm_context(width, numpy.concatenate([above, left]) if is_fc else above, None if is_fc else left)
+    numpy.testing.assert_array_equal(epilogue.epilogue_hm(raw, MEAN), pair)
+    pred, want = _oracle_hm(wts, width, plane, orow, ocol, flags, n_avail)
+    helpers.check_parity(raw, pred)
+
+
+@pytest.mark.parametrize('width', [4, 8])
+def test_hm_context_call_with_trained_conv_nets(engine, golden_dir, width):
+    """A convolutional net loaded for width 4 / 8 serves the flattened-context call (its portions are the two halves of
+    the flattened context, TComPattern.cpp:352-353); checked with the pretrained checkpoints the reference ships."""
+    import os
+    from context_adaptive_neural_network_based_prediction_b200 import Engine, weights as W
+    from oracle import context, nets
+    eng = Engine()
+    try:
+        path = os.path.join(golden_dir, 'conv%d_single.pnnw' % width)
+        eng.load_net(path)
+        _, _, wts = W.load_flat(path)
+        img = numpy.load(os.path.join(golden_dir, 'cliff_luma.npy'))
+        above, left, flat, _ = context.gather_image_blocks(img[None], [0, 0, 0], [width, 40, 96], [width, 64, 120], width, MEAN, 0, 0)
+        for i in range(3):
+            raw = eng.predict_hm_context(width, flat[i])
+            ref = nets.forward_conv(wts, above[i:i + 1], left[i:i + 1])[0, :, :, 0]
+            helpers.check_parity(raw, ref)
+            again = eng.predict_hm_context(width, flat[i])
+            numpy.testing.assert_array_equal(raw, again)
+    finally:
+        eng.close()
