@@ -2,6 +2,8 @@
 // channel-wise merger, last transposed convolution (1 output channel) with the fused epilogue, PSNR.
 #include "kernels_common.cuh"
 
+#include <cstdlib>
+
 namespace pnn {
 
 static inline int grid_for(int64_t n, int block) {
@@ -184,6 +186,140 @@ __global__ void __launch_bounds__(128) gemv_last_kernel(GemvLaunch L) {
         if (L.leaky) s = leaky_relu(s);
         final_store(L.fin, n, s);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused batch-1 FC net (see FcChainLaunch in pnn_internal.h).  Same arithmetic and reduction order as the
+// gemv_fp32_kernel / gemv_last_kernel pair (the two paths give identical bits).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fc_grid_barrier(unsigned long long* counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ULL);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void fc_hidden_layer(const float* __restrict__ wbase, const float* __restrict__ bias, int K, int N,
+                                                const float* xs, float (*red)[17], float* __restrict__ y) {
+    const int cq = threadIdx.x & 3, ks = threadIdx.x >> 2;
+    const int n = blockIdx.x * 16 + cq * 4;
+    const int kper = (K + 63) >> 6;
+    const int k0 = ks * kper;
+    int k1 = k0 + kper;
+    if (k1 > K) k1 = K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = wbase + (int64_t)k0 * N + n;
+    int k = k0;
+    for (; k + 8 <= k1; k += 8, w += 8 * N) {
+        float4 wv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wv[j] = __ldg((const float4*)(w + j * N));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x = xs[k + j];
+            acc[0] = fmaf(x, wv[j].x, acc[0]);
+            acc[1] = fmaf(x, wv[j].y, acc[1]);
+            acc[2] = fmaf(x, wv[j].z, acc[2]);
+            acc[3] = fmaf(x, wv[j].w, acc[3]);
+        }
+    }
+    for (; k < k1; ++k, w += N) {
+        const float4 wv = __ldg((const float4*)w);
+        const float x = xs[k];
+        acc[0] = fmaf(x, wv.x, acc[0]);
+        acc[1] = fmaf(x, wv.y, acc[1]);
+        acc[2] = fmaf(x, wv.z, acc[2]);
+        acc[3] = fmaf(x, wv.w, acc[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[ks][cq * 4 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int nn = blockIdx.x * 16 + threadIdx.x;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s += red[j][threadIdx.x];
+        y[nn] = leaky_relu(s + bias[nn]);
+    }
+}
+
+__global__ void __launch_bounds__(256) fc_chain_kernel(FcChainLaunch L) {
+    __shared__ __align__(16) float xs[1280];
+    __shared__ float red[64][17];
+    const unsigned long long nb = gridDim.x;
+    const unsigned long long base = (L.seq - 1ULL) * 4ULL * nb;
+    // stage the context: mapped pinned host memory -> device memory (CTA 0 only: one PCIe round trip)
+    if (blockIdx.x == 0) {
+        const int n = HM_HEADER_INTS + 5 * L.W * L.W;
+        for (int i = threadIdx.x; i < n; i += 256) L.staged_dev[i] = L.staged_host[i];
+    }
+    fc_grid_barrier(L.counters, base + 1ULL * nb);
+    for (int k = threadIdx.x; k < L.K[0]; k += 256) xs[k] = hm_context_value(L.staged_dev, L.W, L.mean, k);
+    __syncthreads();
+    fc_hidden_layer(L.w[0], L.bias[0], L.K[0], L.N[0], xs, red, L.vec[0]);
+    for (int layer = 1; layer < 3; ++layer) {
+        fc_grid_barrier(L.counters, base + (unsigned long long)(layer + 1) * nb);
+        for (int k = threadIdx.x; k < L.K[layer]; k += 256) xs[k] = __ldcg(L.vec[layer - 1] + k);
+        __syncthreads();
+        fc_hidden_layer(L.w[layer], L.bias[layer], L.K[layer], L.N[layer], xs, red, L.vec[layer]);
+    }
+    fc_grid_barrier(L.counters, base + 4ULL * nb);
+    // last layer: one warp per output (8 per CTA), weights [N][K]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + warp;
+    if (blockIdx.x * 8 < L.N[3]) {
+        for (int k = threadIdx.x; k < L.K[3]; k += 256) xs[k] = __ldcg(L.vec[2] + k);
+        __syncthreads();
+        if (n < L.N[3]) {
+            const float4* w = (const float4*)(L.w[3] + (int64_t)n * L.K[3]);
+            const float4* x4 = (const float4*)xs;
+            float acc = 0.f;
+            for (int i = lane; i < (L.K[3] >> 2); i += 32) {
+                const float4 wv = __ldg(w + i), xv = x4[i];
+                acc = fmaf(xv.x, wv.x, acc);
+                acc = fmaf(xv.y, wv.y, acc);
+                acc = fmaf(xv.z, wv.z, acc);
+                acc = fmaf(xv.w, wv.w, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) final_store(L.fin, n, acc + L.bias[3][n]);
+        }
+    }
+    // completion: every CTA reports; the last one publishes the sequence number to the host
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned long long old = atomicAdd(L.counters + 1, 1ULL);
+        if (old + 1ULL == L.seq * nb) {
+            *L.done_flag = (int)L.seq;
+            __threadfence_system();
+        }
+    }
+}
+
+int launch_fc_chain(const FcChainLaunch& L, cudaStream_t stream) {
+    // 75 CTAs of 256 threads are always co-resident on the 148 SMs of an otherwise idle B200 (the HM process issues
+    // one synchronous call at a time); a plain launch is several microseconds cheaper than a cooperative one
+    static int coop = -1;
+    if (coop < 0) {
+        const char* e = getenv("PNN_FC_CHAIN_COOPERATIVE");
+        coop = e && atoi(e) != 0;
+    }
+    if (coop) {
+        FcChainLaunch copy = L;
+        void* args[] = {(void*)&copy};
+        cudaLaunchCooperativeKernel((const void*)fc_chain_kernel, dim3(FC_CHAIN_CTAS), dim3(256), args, 0, stream);
+    } else {
+        fc_chain_kernel<<<FC_CHAIN_CTAS, 256, 0, stream>>>(L);
+    }
+    return 1;
 }
 
 int launch_gemv(const GemvLaunch& L, cudaStream_t stream) {

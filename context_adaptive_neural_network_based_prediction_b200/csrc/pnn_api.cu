@@ -466,6 +466,12 @@ struct pnn_handle {
     int32_t* d_hm_out_mapped = nullptr;      // device alias of hm_out (mapped pinned memory)
     float* hm_out_raw = nullptr;             // pinned + mapped, 64*64 floats (raw prediction)
     float* d_hm_out_raw_mapped = nullptr;
+    int32_t* d_hm_staged_mapped = nullptr;   // device alias of hm_staged
+    volatile int* hm_flag = nullptr;         // pinned + mapped completion flag of the fused FC kernel
+    int* d_hm_flag_mapped = nullptr;
+    DevBuf d_fc_counters;
+    unsigned long long fc_seq = 0;
+    bool hm_fused_fc = true;
     DevBuf d_hm_staged;
     int hm_width = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -791,7 +797,13 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&h->ev0));
         CUDA_TRY(cudaEventCreate(&h->ev1));
-        CUDA_TRY(cudaMallocHost((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t)));
+        CUDA_TRY(cudaHostAlloc((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t), cudaHostAllocMapped));
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_staged_mapped, h->hm_staged, 0));
+        CUDA_TRY(cudaHostAlloc((void**)&h->hm_flag, 64, cudaHostAllocMapped));
+        *h->hm_flag = 0;
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_flag_mapped, (void*)h->hm_flag, 0));
+        h->d_fc_counters.reserve(2 * sizeof(unsigned long long));
+        CUDA_TRY(cudaMemset(h->d_fc_counters.p, 0, 2 * sizeof(unsigned long long)));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_out, 64 * 64 * sizeof(int32_t), cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_mapped, h->hm_out, 0));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_out_raw, 64 * 64 * sizeof(float), cudaHostAllocMapped));
@@ -845,6 +857,7 @@ void pnn_destroy(pnn_handle* h) {
     if (h->hm_staged) cudaFreeHost(h->hm_staged);
     if (h->hm_out) cudaFreeHost(h->hm_out);
     if (h->hm_out_raw) cudaFreeHost(h->hm_out_raw);
+    if (h->hm_flag) cudaFreeHost((void*)h->hm_flag);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -913,6 +926,12 @@ int pnn_win_flags_device(pnn_handle* h, const double* d_psnr, const double* d_ba
     } catch (const std::exception& e) {
         return fail(h, e);
     }
+    return 0;
+}
+
+int pnn_set_hm_fused(pnn_handle* h, int enabled) {
+    if (!h) return -1;
+    h->hm_fused_fc = enabled != 0;
     return 0;
 }
 
@@ -1130,7 +1149,55 @@ static void enqueue_hm(pnn_handle* h, Net& net, cudaStream_t s) {
 }
 
 // Runs the staged batch-1 prediction of `net` (captures the launch sequence on first use).
+// FC nets: one cooperative kernel per call, completion through a mapped flag
+static void run_hm_fc_fused(pnn_handle* h, Net& net) {
+    for (int i = 0; i < 3; ++i) net.hm_vec[i].reserve(1280 * sizeof(float));
+    FcChainLaunch L{};
+    int layer = 0;
+    for (const Step& st : net.steps) {
+        L.w[layer] = st.is_final ? st.d_w32_t : st.d_w32;
+        L.bias[layer] = st.d_bias;
+        L.K[layer] = st.g.K;
+        L.N[layer] = st.g.N;
+        ++layer;
+    }
+    L.staged_host = h->d_hm_staged_mapped;
+    L.staged_dev = (int32_t*)h->d_hm_staged.p;
+    for (int i = 0; i < 3; ++i) L.vec[i] = (float*)net.hm_vec[i].p;
+    L.fin.i32 = h->d_hm_out_mapped;
+    L.fin.raw = h->d_hm_out_raw_mapped;
+    L.fin.mean = h->mean;
+    L.fin.round_mode = PNN_ROUND_HALF_AWAY;
+    L.counters = (unsigned long long*)h->d_fc_counters.p;
+    L.seq = ++h->fc_seq;
+    L.done_flag = (volatile int*)h->d_hm_flag_mapped;
+    L.W = net.W;
+    L.mean = h->mean;
+    cudaStream_t s = h->stream;
+    if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev0, s));
+    h->launches += launch_fc_chain(L, s);
+    if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev1, s));
+    CUDA_TRY(cudaGetLastError());
+    // spin on the mapped flag; fall back to the stream to surface an error if it never comes
+    const int want = (int)L.seq;
+    long long spins = 0;
+    while (*h->hm_flag != want) {
+        if (++spins > 200000000LL) {
+            CUDA_TRY(cudaStreamSynchronize(s));
+            if (*h->hm_flag != want) throw std::runtime_error("the fused FC kernel did not complete");
+        }
+    }
+    if (h->profiling) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaEventElapsedTime(&h->hm_ms, h->ev0, h->ev1));
+    }
+}
+
 static void run_hm(pnn_handle* h, Net& net) {
+    if (net.is_fc && h->hm_fused_fc) {
+        run_hm_fc_fused(h, net);
+        return;
+    }
     ensure_workspace(net, 1);
     cudaStream_t s = h->stream;
     if (!net.hm_exec || net.hm_exec_precision != h->precision) {

@@ -196,6 +196,27 @@ struct GemvLaunch {
     FinalOut fin;
 };
 int launch_gemv(const GemvLaunch& L, cudaStream_t stream);
+
+// Whole batch-1 FC net in ONE cooperative kernel (75 CTAs, grid barriers between the layers): CTA 0 pulls the
+// staged context from mapped pinned host memory, every layer is the weight-streaming GEMV of gemv_fp32_kernel,
+// the last layer writes the prediction into mapped pinned memory and the last CTA to finish publishes
+// `seq` in a mapped flag the host spins on (no copy nodes, no stream synchronise).
+struct FcChainLaunch {
+    const float* w[4];               // [K][N] fp32; w[3] is transposed to [N][K]
+    const float* bias[4];
+    int K[4], N[4];
+    const int32_t* staged_host;      // device alias of the mapped pinned staging buffer (header + pixels)
+    int32_t* staged_dev;
+    float* vec[3];
+    FinalOut fin;                    // mapped pinned outputs
+    unsigned long long* counters;    // [0] grid-barrier arrivals, [1] completions (monotonic)
+    unsigned long long seq;          // 1, 2, 3, ... per call
+    volatile int* done_flag;         // device alias of the mapped pinned completion flag
+    int W;
+    float mean;
+};
+constexpr int FC_CHAIN_CTAS = 75;    // 1200 hidden units / 16 columns per CTA
+int launch_fc_chain(const FcChainLaunch& L, cudaStream_t stream);
 void small_kernels_init();
 
 int launch_win_flags(const double* psnr, const double* baseline, int64_t n, uint8_t* win, cudaStream_t stream);

@@ -65,6 +65,10 @@ class Engine(object):
     def last_hm_device_ms(self):
         return float(self._lib.pnn_last_hm_device_ms(self._h))
 
+    def set_hm_fused(self, enabled):
+        """In-loop FC nets: fused cooperative kernel (default) or the CUDA-graph GEMV chain."""
+        self._check(self._lib.pnn_set_hm_fused(self._h, int(bool(enabled))))
+
     def set_profiling(self, enabled):
         self._check(self._lib.pnn_set_profiling(self._h, int(bool(enabled))))
 

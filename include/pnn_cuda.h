@@ -135,6 +135,12 @@ int pnn_predict_image_blocks_device(pnn_handle* h, int width, int is_fully_conne
                                     int64_t n, int mask_w, int mask_h,
                                     float* d_out_f32, uint8_t* d_out_u8, double* d_out_psnr, void* cuda_stream);
 
+/*
+ * In-loop FC nets (widths 4, 8): 1 (default) = one fused cooperative kernel per call with completion through a
+ * mapped flag; 0 = four GEMV kernels replayed as a CUDA graph.  Both give identical bits.
+ */
+int pnn_set_hm_fused(pnn_handle* h, int enabled);
+
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t pnn_launch_count(pnn_handle* h);
 

@@ -123,3 +123,28 @@ def test_hm_context_call_with_trained_conv_nets(engine, golden_dir, width):
             numpy.testing.assert_array_equal(raw, again)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize('width', [4, 8])
+def test_hm_fused_fc_kernel_equals_gemv_chain(engine, weights_dir, width):
+    """The fused cooperative kernel and the CUDA-graph GEMV chain use the same arithmetic and reduction order."""
+    path, _ = helpers.make_net_file(weights_dir, width, True, seed=70 + width, gain=helpers.GAIN[(width, True)])
+    engine.load_net(path)
+    plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 11).astype(numpy.int32)
+    units = 2 * width // 4
+    results = []
+    try:
+        for fused in (True, False, True):
+            engine.set_hm_fused(fused)
+            outs = []
+            for shift in range(4):
+                flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+                if shift & 1:
+                    flags[:units // 2] = 0
+                engine.set_context(width, plane, width + 1 + shift, width + 2 + shift, flags, int(flags.sum()))
+                outs.append(engine.predict_hm(width).copy())
+            results.append(numpy.stack(outs))
+    finally:
+        engine.set_hm_fused(True)
+    numpy.testing.assert_array_equal(results[0], results[1])
+    numpy.testing.assert_array_equal(results[0], results[2])

@@ -6,7 +6,10 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import helpers
 from context_adaptive_neural_network_based_prediction_b200 import Engine, weights
 cpu = '--cpu' in sys.argv
+fused = '--no-fused' not in sys.argv
 eng = Engine(); tmp = tempfile.mkdtemp()
+eng.set_hm_fused(fused)
+if "--prof" in sys.argv: eng.set_profiling(True)
 params = {4: 2998816, 8: 3344464, 16: 1339073, 32: 5622657, 64: 20652545}
 print('%3s %10s %10s %12s %12s' % ('W', 'wall_us', 'device_us', 'GB/s(params)', 'cpu_oracle_us'))
 for width in (4, 8, 16, 32, 64):
@@ -40,5 +43,5 @@ for width in (4, 8, 16, 32, 64):
         for _ in range(20):
             nets.forward(wts, width, is_fc, args)
         cpu_us = (time.perf_counter() - t0) / 20 * 1e6
-    d = float(numpy.median(dev)) * 1e3
+    d = max(float(numpy.median(dev)) * 1e3, 1e-9)
     print('%3d %10.1f %10.1f %12.1f %12.1f' % (width, wall, d, params[width] * 4 / (d * 1e-6) / 1e9, cpu_us), flush=True)
