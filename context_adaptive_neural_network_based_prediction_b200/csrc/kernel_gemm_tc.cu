@@ -180,8 +180,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_nt = (g.N + TC_BN - 1) / TC_BN;
     const int num_mt = (L.M + TC_BM - 1) / TC_BM;
-    const int num_tiles = num_nt * num_mt;
     const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+    // split-K: tile = (ks, mt, nt) with nt fastest; slice ks owns the K blocks [ks*kb_per, min(num_kb, (ks+1)*kb_per))
+    const int split_k = L.split_k > 1 ? L.split_k : 1;
+    const int kb_per = (num_kb + split_k - 1) / split_k;
+    const int mn_tiles = num_nt * num_mt;
+    const int num_tiles = mn_tiles * split_k;
     // the widest tile fixes the stage size, hence the ring depth
     const int bn_max = g.N >= TC_BN ? TC_BN : ((g.N + 15) & ~15);
     const uint32_t stage_bytes = 2u * A_PLANE + 2u * (uint32_t)bn_max * 128u;
@@ -229,7 +233,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
         int64_t rbase[8];
         int rpos[8];
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile / num_nt;
+            const int ks = tile / mn_tiles;
+            const int mt = (tile - ks * mn_tiles) / num_nt;
+            const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
             if (mt != cur_mt) {
                 cur_mt = mt;
                 RowIter it = row_init(rs16, (unsigned)(mt * TC_BM + rgrp));
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
                     row_advance(rs16, it);
                 }
             }
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(empty(s), ph ^ 1u);
                 const int k = kb * TC_BK + c * 8;
                 const bool k_ok = k < g.K;
@@ -277,12 +283,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nt = tile % num_nt;
+                const int ks = tile / mn_tiles;
+                const int nt = (tile - ks * mn_tiles) % num_nt;
+                const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
                 int bn = g.N - nt * TC_BN;
                 bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
                 const uint32_t b_bytes = 2u * (uint32_t)bn * 128u;
                 const uint8_t* src = L.w_tiles + (size_t)nt * num_kb * (2u * TC_BN * 128u);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty(s), ph ^ 1u);
                     if (L.debug_flags & 2) {
                         mbar_arrive(full_b(s));
@@ -300,7 +308,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
         uint32_t ph = 0;
         int lt = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int nt = tile % num_nt;
+            const int ks = tile / mn_tiles;
+            const int nt = (tile - ks * mn_tiles) % num_nt;
+            const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
             int bn = g.N - nt * TC_BN;
             bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
             // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
             const uint32_t acc = tmem_base + (uint32_t)(ab * TC_BN);
             mbar_wait(tmem_empty(ab), (((uint32_t)lt >> 1) & 1u) ^ 1u);     // the epilogue drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(full_a(s), ph);
                 mbar_wait(full_b(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -331,17 +341,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
                     for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
                         if (k4 < ksteps) {                      // +2 per K step: 32 bytes >> 4 inside the 128-byte swizzle row
                             if (merged) {
-                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc2, (kb | k4) != 0 ? 1u : 0u);   // [hi*hi | hi*lo]
+                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc2, (kb > kb0 || k4 > 0) ? 1u : 0u);   // [hi*hi | hi*lo]
                                 umma_bf16(acc, da_lo + 2 * k4, db_hi + 2 * k4, idesc, 1u);                          // lo*hi
                             } else {
-                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
                                 umma_bf16(acc, da_hi + 2 * k4, db_lo + 2 * k4, idesc, 1u);
                                 umma_bf16(acc, da_lo + 2 * k4, db_hi + 2 * k4, idesc, 1u);
                             }
                         }
                     }
                     umma_commit(empty(s));
-                    if (kb == num_kb - 1) umma_commit(tmem_full(ab));
+                    if (kb == kb1 - 1) umma_commit(tmem_full(ab));
                 }
                 __syncwarp();
                 if (++s == num_stages) { s = 0; ph ^= 1u; }
@@ -358,7 +368,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
         const RowStep rs1 = make_row_step(g, 1u);
         int j = 0;                                           // tiles this set has processed
         for (int tile = blockIdx.x + set * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, ++j) {
-            const int nt = tile % num_nt, mt = tile / num_nt;
+            const int ks = tile / mn_tiles;
+            const int nt = (tile - ks * mn_tiles) % num_nt, mt = (tile - ks * mn_tiles) / num_nt;
             const int n0 = nt * TC_BN;
             int bn = g.N - n0;
             bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
@@ -399,6 +410,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
                 int nvalid = g.N - nbase;                    // multiple of 16 by construction
                 if (nvalid > 32) nvalid = 32;
                 if (L.debug_flags & 4) continue;
+                if (split_k > 1) {
+                    // raw accumulators of this K slice; bias / activation / split happen in splitk_reduce_kernel
+                    if (m_own < L.M) {
+                        float4* dst = (float4*)(L.partial + ((size_t)ks * L.M + m_own) * g.N + nbase);
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            if (jj * 4 < nvalid) {
+                                dst[jj] = make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]),
+                                                      __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3]));
+                            }
+                        }
+                    }
+                    continue;
+                }
                 if (L.out_mode == OUT_FINAL) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) {
@@ -467,7 +492,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
     }
 }
 
+// Sums the K slices in ascending order (fixed), then bias, LeakyReLU and the hi/lo split.  Thread = (row, 8 columns).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmLaunch L) {
+    const GemmGeom& g = L.g;
+    const int groups = g.N >> 3;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= L.M * groups) return;
+    const int m = idx / groups, n = (idx - m * groups) << 3;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int ks = 0; ks < L.split_k; ++ks) {
+        const float4* p = (const float4*)(L.partial + ((size_t)ks * L.M + m) * g.N + n);
+        const float4 a = p[0], b = p[1];
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        float f0 = acc[2 * jj] + L.bias[n + 2 * jj], f1 = acc[2 * jj + 1] + L.bias[n + 2 * jj + 1];
+        if (g.leaky) {
+            f0 = leaky_relu(f0);
+            f1 = leaky_relu(f1);
+        }
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(f0, h0, l0);
+        split_bf16(f1, h1, l1);
+        hi[jj] = pack_bf16(h0, h1);
+        lo[jj] = pack_bf16(l0, l1);
+    }
+    const RowStep rs = make_row_step(g, 1u);
+    const int64_t o = out_offset(g, row_init(rs, (unsigned)m)) + n;
+    *(uint4*)((__nv_bfloat16*)L.out.p0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *(uint4*)((__nv_bfloat16*)L.out.p1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 }  // namespace
+
+int launch_splitk_reduce(const GemmLaunch& L, cudaStream_t stream) {
+    const int total = L.M * (L.g.N >> 3);
+    splitk_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(L);
+    return 1;
+}
 
 cudaError_t gemm_tc_init() {
     return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -485,7 +550,7 @@ int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) {
     }
     const int num_nt = (L.g.N + TC_BN - 1) / TC_BN;
     const int num_mt = (L.M + TC_BM - 1) / TC_BM;
-    const long long tiles = (long long)num_nt * num_mt;
+    const long long tiles = (long long)num_nt * num_mt * (L.split_k > 1 ? L.split_k : 1);
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);   // persistent: one CTA per SM
     gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(L);
     return 1;

@@ -469,9 +469,11 @@ struct pnn_handle {
     int32_t* d_hm_staged_mapped = nullptr;   // device alias of hm_staged
     volatile int* hm_flag = nullptr;         // pinned + mapped completion flag of the fused FC kernel
     int* d_hm_flag_mapped = nullptr;
+    DevBuf d_splitk;                         // split-K partial sums of the in-loop conv calls
     DevBuf d_fc_counters;
     unsigned long long fc_seq = 0;
     bool hm_fused_fc = true;
+    bool hm_split_k = true;
     DevBuf d_hm_staged;
     int hm_width = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -570,7 +572,7 @@ Act act_of(Net& net, int buf) {
 }
 
 // Runs every layer of `net` on `n` samples whose contexts are already in the input buffers.
-void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream_t stream) {
+void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream_t stream, bool allow_split_k = false) {
     const bool split = h->precision == PNN_PRECISION_BF16X3;
     for (const Step& st : net.steps) {
         switch (st.kind) {
@@ -589,8 +591,25 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.w_fp32 = st.d_w32;
                 L.w_tiles = st.d_wt;
                 L.bias = st.d_bias;
+                L.split_k = 1;
+                if (allow_split_k && split && !st.is_final) {
+                    // in-loop batch-1 call: spread the K blocks of the few tiles over the SMs (fixed slicing)
+                    const int tiles = tc_num_nt(st.g.N) * ((L.M + TC_BM - 1) / TC_BM);
+                    const int num_kb = tc_num_kb(st.g.K);
+                    if (tiles <= 32 && num_kb >= 4) {
+                        int kb_per = (num_kb * tiles + 147) / 148;
+                        if (kb_per < 2) kb_per = 2;
+                        const int slices = (num_kb + kb_per - 1) / kb_per;
+                        const size_t need_bytes = (size_t)slices * L.M * st.g.N * sizeof(float);
+                        if (slices > 1 && need_bytes <= h->d_splitk.bytes) {
+                            L.split_k = slices;
+                            L.partial = (float*)h->d_splitk.p;
+                        }
+                    }
+                }
                 ProfScope ps(h, stream, split ? "gemm_tc" : "gemm_fp32", L.M, st.g.N, st.g.K, true);
                 h->launches += split ? launch_gemm_tc(L, stream) : launch_gemm_fp32(L, stream);
+                if (L.split_k > 1) h->launches += launch_splitk_reduce(L, stream);
                 break;
             }
             case STEP_CONV0: {
@@ -802,6 +821,7 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_flag, 64, cudaHostAllocMapped));
         *h->hm_flag = 0;
         CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_flag_mapped, (void*)h->hm_flag, 0));
+        h->d_splitk.reserve((size_t)64 << 20);
         h->d_fc_counters.reserve(2 * sizeof(unsigned long long));
         CUDA_TRY(cudaMemset(h->d_fc_counters.p, 0, 2 * sizeof(unsigned long long)));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_out, 64 * 64 * sizeof(int32_t), cudaHostAllocMapped));
@@ -932,6 +952,8 @@ int pnn_win_flags_device(pnn_handle* h, const double* d_psnr, const double* d_ba
 int pnn_set_hm_fused(pnn_handle* h, int enabled) {
     if (!h) return -1;
     h->hm_fused_fc = enabled != 0;
+    h->hm_split_k = enabled != 0;            // both in-loop optimisations follow the switch (0 = plain kernels)
+    for (auto& kv : h->nets) kv.second->drop_hm_graph();
     return 0;
 }
 
@@ -1140,7 +1162,7 @@ static void enqueue_hm(pnn_handle* h, Net& net, cudaStream_t s) {
         G.split = 0;
         launches += launch_gather_hm(G, s);
         const int64_t before = h->launches;
-        run_net(h, net, 1, fin, s);
+        run_net(h, net, 1, fin, s, /*allow_split_k=*/h->hm_split_k);
         launches += (int)(h->launches - before);
         h->launches = before;
     }

@@ -63,7 +63,13 @@ struct GemmLaunch {
     const uint8_t* w_tiles;     // pre-swizzled bf16 hi/lo tiles (bf16x3 precision)
     const float* bias;          // [N]
     int debug_flags;            // tuning aid: bit 0 skip A loads, bit 1 skip B loads, bit 2 skip epilogue stores
+    // split-K (in-loop batch-1 path only, where 1-2 tiles would otherwise walk K serially): slice ks of the K blocks
+    // writes its raw fp32 accumulators to partial[ks][M][N]; splitk_reduce adds the slices in ascending order, then
+    // bias / LeakyReLU / hi-lo split.  1 = off.
+    int split_k;
+    float* partial;
 };
+int launch_splitk_reduce(const GemmLaunch& L, cudaStream_t stream);
 
 // bf16x3 weight tiling (see DESIGN.md "weight tiles"): N is cut in tiles of TC_BN rows (the last one
 // narrower, a multiple of 16), K in blocks of 64.  Tile (nt, kb) is stored as the exact shared-memory

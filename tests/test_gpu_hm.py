@@ -148,3 +148,31 @@ def test_hm_fused_fc_kernel_equals_gemv_chain(engine, weights_dir, width):
         engine.set_hm_fused(True)
     numpy.testing.assert_array_equal(results[0], results[1])
     numpy.testing.assert_array_equal(results[0], results[2])
+
+
+@pytest.mark.parametrize('width', [16, 64])
+def test_hm_split_k_matches_plain_kernels(engine, weights_dir, width):
+    """In-loop conv calls: split-K with a fixed-order reduction (default) against the plain batch-1 kernels: both within the
+    parity bound of the oracle, each deterministic."""
+    path, wts = helpers.make_net_file(weights_dir, width, False, seed=80 + width, gain=helpers.GAIN[(width, False)])
+    engine.load_net(path)
+    engine.set_precision('bf16x3')
+    plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 13).astype(numpy.int32)
+    units = 2 * width // 4
+    flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+    n_avail = int(flags.sum())
+    pred, want = _oracle_hm(wts, width, plane, width + 3, width + 5, flags, n_avail)
+    outs = {}
+    try:
+        for mode in (True, False):
+            engine.set_hm_fused(mode)
+            engine.set_context(width, plane, width + 3, width + 5, flags, n_avail)
+            a = engine.predict_hm(width)
+            engine.set_context(width, plane, width + 3, width + 5, flags, n_avail)
+            b = engine.predict_hm(width)
+            numpy.testing.assert_array_equal(a, b)
+            assert numpy.abs(a - want).max() <= 1 and (a == want).mean() >= 0.999
+            outs[mode] = a
+    finally:
+        engine.set_hm_fused(True)
+    assert numpy.abs(outs[True] - outs[False]).max() <= 1
