@@ -105,14 +105,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format): start address >> 4 in
-// bits [0,14), leading byte offset (unused for swizzled K-major, 1) in [16,30), stride byte offset
-// = 1024 B between 8-row groups in [32,46), descriptor version 1 in [46,48), layout SWIZZLE_128B = 2
-// in [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }

@@ -1,5 +1,6 @@
-// HBM-bound kernels of the PNN path: fused context gather, first convolution (1 input channel),
-// channel-wise merger, last transposed convolution (1 output channel) with the fused epilogue, PSNR.
+// HBM / latency-bound kernels of the PNN path: fused context gathers, im2col of the first convolution, channel-wise
+// merger, col2im of the last transposed convolution with the fused epilogue, PSNR / win flags, and the batch-1
+// fully-connected kernels of the in-loop path.
 #include "kernels_common.cuh"
 
 #include <cstdlib>
@@ -344,97 +345,6 @@ int launch_convert_input(const float* src, Act dst, int64_t n, int split, cudaSt
 }
 
 // ---------------------------------------------------------------------------------------------
-// First convolution of a branch: 1 input channel, k x k, stride s, SAME padding, + bias, LeakyReLU
-// (reference pnn/components.py:33-46, pnn/tfutils.py:134-139).  One thread per output value, the
-// output channel fastest so that the k*k input pixels are warp broadcasts and the stores coalesce.
-// ---------------------------------------------------------------------------------------------
-// v2: a CTA of 256 threads computes 64 output pixels x all output channels of one sample; thread =
-// (pixel, group of Cout/4 channels).  The k*k input pixels are read once into registers, the weights sit in
-// shared memory (the 4 channel groups of a warp read 4 distinct 16-byte words: conflict-free broadcasts),
-// and each thread stores its channels with 16-byte vectors.
-template <bool SPLIT, int CPT /*channels per thread*/, int KK /*k*k*/>
-__global__ void __launch_bounds__(256) conv0_kernel(Conv0Launch L) {
-    __shared__ float w_s[KK * CPT * 4];
-    __shared__ float b_s[CPT * 4];
-    const int Cout = CPT * 4;
-    for (int i = threadIdx.x; i < KK * Cout; i += 256) w_s[i] = L.w[i];
-    if (threadIdx.x < Cout) b_s[threadIdx.x] = L.bias[threadIdx.x];
-    __syncthreads();
-    const int P = L.OH * L.OW;
-    const int tiles = (P + 63) >> 6;
-    const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
-    const int pix = (tile << 6) + (threadIdx.x >> 2);
-    const int cg = threadIdx.x & 3;
-    if (pix >= P) return;
-    const int oy = pix / L.OW, ox = pix - oy * L.OW;
-    const float* in = L.in + (int64_t)b * L.IH * L.IW;
-    const int k = L.k;
-    float x[KK];
-#pragma unroll
-    for (int t = 0; t < KK; ++t) {
-        const int ky = t / k, kx = t - ky * k;      // k is 3 or 5: KK is a compile-time 9 or 25
-        const int iy = oy * L.stride + ky - L.pad, ix = ox * L.stride + kx - L.pad;
-        x[t] = (iy >= 0 && iy < L.IH && ix >= 0 && ix < L.IW) ? __ldg(in + iy * L.IW + ix) : 0.f;
-    }
-    float acc[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int t = 0; t < KK; ++t) {
-        const float4* wr = (const float4*)(w_s + t * Cout + cg * CPT);
-#pragma unroll
-        for (int q = 0; q < CPT / 4; ++q) {
-            const float4 w4 = wr[q];
-            acc[4 * q + 0] = fmaf(x[t], w4.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(x[t], w4.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(x[t], w4.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(x[t], w4.w, acc[4 * q + 3]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) acc[j] = leaky_relu(acc[j] + b_s[cg * CPT + j]);
-    const int64_t o = ((int64_t)b * P + pix) * Cout + cg * CPT;
-    if (SPLIT) {
-        uint32_t hi[CPT / 2], lo[CPT / 2];
-#pragma unroll
-        for (int j = 0; j < CPT / 2; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(acc[2 * j], h0, l0);
-            split_bf16(acc[2 * j + 1], h1, l1);
-            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        uint4* ph = (uint4*)((__nv_bfloat16*)L.out.p0 + o);
-        uint4* pl = (uint4*)((__nv_bfloat16*)L.out.p1 + o);
-#pragma unroll
-        for (int q = 0; q < CPT / 8; ++q) {
-            ph[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-            pl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-        }
-    } else {
-        float4* po = (float4*)((float*)L.out.p0 + o);
-#pragma unroll
-        for (int q = 0; q < CPT / 4; ++q) po[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-    }
-}
-
-template <bool SPLIT>
-static int launch_conv0_t(const Conv0Launch& L, cudaStream_t stream) {
-    const int P = L.OH * L.OW;
-    const int64_t grid = (int64_t)L.n * ((P + 63) / 64);
-    if (L.Cout == 64 && L.k == 5) conv0_kernel<SPLIT, 16, 25><<<(unsigned)grid, 256, 0, stream>>>(L);
-    else if (L.Cout == 32 && L.k == 3) conv0_kernel<SPLIT, 8, 9><<<(unsigned)grid, 256, 0, stream>>>(L);
-    else return -1;
-    return 1;
-}
-
-int launch_conv0(const Conv0Launch& L, cudaStream_t stream) {
-    if (L.n == 0) return 0;
-    // reference pnn/PredictionNeuralNetwork.py:126-132: the first stride is 2 (k = 5, 64 maps) except for W = 4 (k = 3, 32 maps)
-    return L.split ? launch_conv0_t<true>(L, stream) : launch_conv0_t<false>(L, stream);
-}
-
-// ---------------------------------------------------------------------------------------------
 // im2col for the first convolution (1 input channel): thread = (output pixel, group of 8 taps).  The
 // convolution itself then runs on the tensor cores as a GEMM with K = KP (reference pnn/tfutils.py:134-139).
 // ---------------------------------------------------------------------------------------------
@@ -677,78 +587,6 @@ int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
     if (groups < 1) groups = 1;
     if (L.split) merger_kernel<true><<<ncg * groups, 256, MG_SMEM, stream>>>(L, groups);
     else merger_kernel<false><<<ncg * groups, 256, MG_SMEM, stream>>>(L, groups);
-    return 1;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Last transposed convolution: Cin -> 1 channel, linear, fused with the output epilogue
-// (reference pnn/components.py:237-259, pnn/tfutils.py:455-462; epilogue TComPrediction.cpp:621-635 /
-// tools/tools.py:49).  Gather form with a fixed tap order (ky, kx, ci ascending):
-//   out[y, x] = bias + sum_{ky,kx : (y+pad-ky) % s == 0 ...} in[(y+pad-ky)/s, (x+pad-kx)/s, :] . w[ky, kx, :]
-// One thread per output pixel.
-// ---------------------------------------------------------------------------------------------
-// v2: one CTA per (sample, 128 output pixels), weights in shared memory, 32-bit index arithmetic.
-template <bool SPLIT>
-__global__ void __launch_bounds__(128) tconv_last_kernel(TconvLastLaunch L) {
-    extern __shared__ float w_s[];                       // [k*k][Cin]
-    for (int i = threadIdx.x; i < L.k * L.k * L.Cin; i += 128) w_s[i] = L.w[i];
-    __syncthreads();
-    const int OH = L.IH * L.stride, OW = L.IW * L.stride, P = OH * OW;
-    const int tiles = (P + 127) >> 7;
-    const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
-    const int pix = (tile << 7) + threadIdx.x;
-    if (pix >= P) return;
-    const int y = pix / OW, x = pix - y * OW;
-    const int64_t in_base = (int64_t)b * L.IH * L.IW * L.Cin;
-    float acc = 0.f;
-    for (int ky = 0; ky < L.k; ++ky) {
-        const int ty = y + L.pad - ky;
-        if (ty < 0 || (L.stride == 2 && (ty & 1))) continue;
-        const int iy = L.stride == 2 ? ty >> 1 : ty;
-        if (iy >= L.IH) continue;
-        for (int kx = 0; kx < L.k; ++kx) {
-            const int tx = x + L.pad - kx;
-            if (tx < 0 || (L.stride == 2 && (tx & 1))) continue;
-            const int ix = L.stride == 2 ? tx >> 1 : tx;
-            if (ix >= L.IW) continue;
-            const int64_t base = in_base + (int64_t)(iy * L.IW + ix) * L.Cin;
-            const float* w = w_s + (ky * L.k + kx) * L.Cin;
-            if (SPLIT) {
-                const uint4* ph = (const uint4*)((const __nv_bfloat16*)L.in.p0 + base);
-                const uint4* pl = (const uint4*)((const __nv_bfloat16*)L.in.p1 + base);
-                for (int ci = 0; ci < L.Cin; ci += 8) {
-                    const uint4 h = __ldg(ph + (ci >> 3)), l = __ldg(pl + (ci >> 3));
-                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float a0 = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                        const float a1 = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
-                        acc = fmaf(a0, w[ci + 2 * j], acc);
-                        acc = fmaf(a1, w[ci + 2 * j + 1], acc);
-                    }
-                }
-            } else {
-                const float4* p = (const float4*)((const float*)L.in.p0 + base);
-                for (int ci = 0; ci < L.Cin; ci += 4) {
-                    const float4 a = __ldg(p + (ci >> 2));
-                    acc = fmaf(a.x, w[ci], acc);
-                    acc = fmaf(a.y, w[ci + 1], acc);
-                    acc = fmaf(a.z, w[ci + 2], acc);
-                    acc = fmaf(a.w, w[ci + 3], acc);
-                }
-            }
-        }
-    }
-    final_store(L.fin, (int64_t)b * P + pix, acc + L.bias);
-}
-
-int launch_tconv_last(const TconvLastLaunch& L, cudaStream_t stream) {
-    if (L.n == 0) return 0;
-    const int P = L.IH * L.stride * L.IW * L.stride;
-    const int64_t grid = (int64_t)L.n * ((P + 127) / 128);
-    const size_t smem = (size_t)L.k * L.k * L.Cin * sizeof(float);
-    if (L.split) tconv_last_kernel<true><<<(unsigned)grid, 128, smem, stream>>>(L);
-    else tconv_last_kernel<false><<<(unsigned)grid, 128, smem, stream>>>(L);
     return 1;
 }
 

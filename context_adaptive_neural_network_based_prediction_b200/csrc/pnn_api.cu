@@ -84,7 +84,7 @@ T* upload(const std::vector<T>& v, std::vector<std::unique_ptr<DevBuf>>& keep) {
     return (T*)keep.back()->p;
 }
 
-enum StepKind { STEP_GEMM, STEP_CONV0, STEP_MERGER, STEP_TCONV_LAST, STEP_IM2COL, STEP_COL2IM };
+enum StepKind { STEP_GEMM, STEP_MERGER, STEP_IM2COL, STEP_COL2IM };
 
 struct Step {
     StepKind kind;
@@ -612,18 +612,6 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 if (L.split_k > 1) h->launches += launch_splitk_reduce(L, stream);
                 break;
             }
-            case STEP_CONV0: {
-                Conv0Launch L{};
-                L.in = (const float*)net.ws0[st.in0]->p;
-                L.out = act_of(net, st.out);
-                L.w = st.d_w32;
-                L.bias = st.d_bias;
-                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.OH = st.OH; L.OW = st.OW; L.Cout = st.C;
-                L.k = st.k; L.stride = st.stride; L.pad = st.pad; L.split = split;
-                ProfScope ps(h, stream, "conv0", n * st.OH * st.OW, st.C, st.k * st.k, false);
-                h->launches += launch_conv0(L, stream);
-                break;
-            }
             case STEP_MERGER: {
                 MergerLaunch L{};
                 L.in0 = act_of(net, st.in0);
@@ -655,19 +643,6 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.split = split;
                 ProfScope ps(h, stream, "col2im", n * st.IH * st.stride * st.IW * st.stride, 1, 9, false);
                 h->launches += launch_col2im(L, stream);
-                break;
-            }
-            case STEP_TCONV_LAST: {
-                TconvLastLaunch L{};
-                L.in = act_of(net, st.in0);
-                L.w = st.d_w32;
-                L.bias = st.bias_scalar;
-                L.fin = fin;
-                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.Cin = st.C; L.k = st.k; L.stride = st.stride; L.pad = st.pad;
-                L.split = split;
-                ProfScope ps(h, stream, "tconv_last", n * st.IH * st.stride * st.IW * st.stride, 1,
-                             (int64_t)st.C * ((st.k + st.stride - 1) / st.stride) * ((st.k + st.stride - 1) / st.stride), false);
-                h->launches += launch_tconv_last(L, stream);
                 break;
             }
         }

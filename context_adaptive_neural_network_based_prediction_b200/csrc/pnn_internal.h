@@ -103,17 +103,6 @@ int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);
 // one-time opt-in for the tcgen05 kernel's dynamic shared memory
 cudaError_t gemm_tc_init();
 
-// First convolution of a branch (one input channel, reference pnn/components.py:33-46 with i == 0).
-struct Conv0Launch {
-    const float* in;     // [n, IH, IW] fp32 context portion
-    Act out;             // [n, OH, OW, Cout]
-    const float* w;      // [k*k][Cout]
-    const float* bias;
-    int n, IH, IW, OH, OW, Cout, k, stride, pad;
-    int split;           // 1: write hi/lo bf16 planes
-};
-int launch_conv0(const Conv0Launch& L, cudaStream_t stream);
-
 // im2col of a one-channel context portion for the first convolution: row (b, oy, ox) gets the k*k taps
 // (zero outside the map, SAME padding) followed by zeros up to KP columns.
 struct Im2colLaunch {
@@ -142,16 +131,6 @@ struct MergerLaunch {
     int n, C, split;
 };
 int launch_merger(const MergerLaunch& L, cudaStream_t stream);
-
-// Last transposed convolution (one output channel, linear) with the fused epilogue.
-struct TconvLastLaunch {
-    Act in;              // [n, IH, IW, Cin]
-    const float* w;      // [k*k][Cin]  (w_tf[ky][kx][0][ci])
-    float bias;
-    FinalOut fin;
-    int n, IH, IW, Cin, k, stride, pad, split;
-};
-int launch_tconv_last(const TconvLastLaunch& L, cudaStream_t stream);
 
 // Fused gather: uint8 image -> mean-centred, masked context (reference sets/common.py:99-109, 454-472).
 struct GatherLaunch {
