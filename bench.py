@@ -82,7 +82,7 @@ class ClockSampler(object):
                 ['nvidia-smi', '-i', str(index),
                  '--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
                  'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '200'],
+                 'clocks_event_reasons.sw_power_cap', '--format=csv,noheader,nounits', '-lms', '50'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -381,7 +381,11 @@ def main():
         achieved = prof['gemm_flops'] / (prof['gemm_ms'] * 1e-3) / 1e12 if prof['gemm_ms'] > 0 else 0.
         roofline = {
             'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 bf16x3 implicit GEMM)', 'achieved': achieved, 'peak': peak,
-            'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+            'unit': 'TFLOP/s', 'frac': achieved / peak,
+            # DRAM read + write bytes of one launch from the committed `ncu --set full` capture (profiles/): FC-4 hidden layer,
+            # M = 386377 rows, N = K = 1200; its algorithmic bytes (A hi+lo read once + hi/lo output) are 3.709e9
+            'traffic': 3.677e9, 'traffic_launch': 'gemm_tc_kernel M=386377 N=1200 K=1200 (profiles/r1_gemm_tc_full_summary.txt)',
+            'traffic_algorithmic_bytes': 3.709e9,
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks
                            else 'fallback 1.59 PFLOP/s (B200_PROFILING.md)',
             'mma_passes': 3, 'frac_of_tensor_issue': 3. * achieved / peak,
