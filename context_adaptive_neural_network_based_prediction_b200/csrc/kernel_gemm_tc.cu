@@ -12,10 +12,12 @@
 // Persistent kernel: one CTA per SM, tiles (128 rows x up to 256 columns) taken round-robin
 // (tile = blockIdx.x + i*gridDim.x, n-tile fastest so that concurrent CTAs share the A rows in L2).
 // Warp roles (320 threads):
-//   warps 0-3  A producers: implicit-GEMM gather of 16-byte (8-channel) chunks with cp.async straight
-//              into the 128-byte-swizzled K-major shared-memory layout, zero-filling SAME padding,
-//              transposed-convolution borders, K tails and M tails; completion is signalled with
-//              cp.async.mbarrier.arrive.noinc.
+//   warps 0-3  A producers.  Real convolutions (more than one tap, Cin % 64 == 0): the M tile is a box of
+//              bw x bh output pixels x nb samples and ONE thread issues two cp.async.bulk.tensor (TMA, rank-4
+//              NHWC tensor map, hardware 128B swizzle, out-of-bounds zero fill = SAME padding / tconv borders,
+//              element strides for stride 2) per K block.  Other layers (FC, 1x1, K tails): implicit-GEMM
+//              gather of 16-byte (8-channel) chunks with cp.async straight into the 128-byte-swizzled K-major
+//              layout, zero-filling K and M tails; completion via cp.async.mbarrier.arrive.noinc.
 //   warp 4     B producer: one cp.async.bulk per stage; the weights were pre-tiled on the host as the
 //              exact shared-memory image (hi plane then lo plane), so no tensor map is needed.
 //   warp 5     TMEM allocation (512 columns = two accumulators) + single-thread MMA issue;
@@ -27,6 +29,10 @@
 //   (warps 6-7 idle: they keep the epilogue sets aligned on warpgroups / TMEM lane quarters)
 // The smem ring has 2-4 stages depending on the tile width (A 32 KB + B 2*bn*128 B per stage).
 #include "kernels_common.cuh"
+
+#include <cuda.h>
+
+#include <cstdlib>
 
 namespace pnn {
 
@@ -85,6 +91,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t adesc_lo, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
         "}" ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -155,7 +166,8 @@ __device__ __forceinline__ int64_t out_offset(const GemmGeom& g, const RowIter& 
            ((int64_t)((int)it.oy * g.osy + g.ooy) * g.OWf + ((int)it.ox * g.osx + g.oox)) * g.N;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, const __grid_constant__ CUtensorMap tmap_hi,
+                                                                   const __grid_constant__ CUtensorMap tmap_lo) {
     extern __shared__ uint8_t smem_raw[];
     const GemmGeom& g = L.g;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -171,7 +183,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_nt = (g.N + TC_BN - 1) / TC_BN;
-    const int num_mt = (L.M + TC_BM - 1) / TC_BM;
+    // TMA mode: an M tile is a box of (1 << bw_log2) x (1 << bh_log2) output pixels x nb samples
+    const int box_shift = L.bw_log2 + L.bh_log2;
+    const int nb_box = TC_BM >> box_shift;
+    const int n_samples = L.M / g.P;
+    const int num_mt = L.tma ? ((n_samples + nb_box - 1) / nb_box) * L.y_tiles * L.x_tiles : (L.M + TC_BM - 1) / TC_BM;
     const int num_kb = (g.K + TC_BK - 1) / TC_BK;
     // split-K: tile = (ks, mt, nt) with nt fastest; slice ks owns the K blocks [ks*kb_per, min(num_kb, (ks+1)*kb_per))
     const int split_k = L.split_k > 1 ? L.split_k : 1;
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
-            mbar_init(full_a(s), 128);
+            mbar_init(full_a(s), L.tma ? 1 : 128);
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
@@ -211,7 +227,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp < 4) {
+    if (warp < 4 && L.tma) {
+        // ------------------------------------------------------------------ A producer, TMA: one thread, two box loads per K block
+        if (threadIdx.x == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_lo) : "memory");
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int ks = tile / mn_tiles;
+                int r = (tile - ks * mn_tiles) / num_nt;
+                const int xt = r % L.x_tiles;
+                r /= L.x_tiles;
+                const int yt = r % L.y_tiles, bt = r / L.y_tiles;
+                const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+                const int ox0 = xt << L.bw_log2, oy0 = yt << L.bh_log2;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty(s), ph ^ 1u);
+                    const int k = kb * TC_BK;
+                    const int tap = k / g.Cin, ci = k - tap * g.Cin;
+                    const int ty = tap / g.TW, tx = tap - ty * g.TW;
+                    const int c1 = ox0 * g.sx_o + tx * g.sx_t + g.cx, c2 = oy0 * g.sy_o + ty * g.sy_t + g.cy;
+                    const uint32_t a_hi = smem_base + s * stage_bytes;
+                    if (L.debug_flags & 1) {
+                        mbar_arrive(full_a(s));
+                    } else {
+                        mbar_arrive_expect_tx(full_a(s), 2u * A_PLANE);
+                        tma_load_4d(a_hi, &tmap_hi, ci, c1, c2, bt * nb_box, full_a(s));
+                        tma_load_4d(a_hi + A_PLANE, &tmap_lo, ci, c1, c2, bt * nb_box, full_a(s));
+                    }
+                    if (++s == num_stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp < 4) {
         // ------------------------------------------------------------------ A producers
         const int c = threadIdx.x & 7;          // 16-byte chunk (8 channels) inside the 64-wide k block
         const int rgrp = threadIdx.x >> 3;      // rows rgrp + 16*i
@@ -365,11 +414,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L) {
             const int n0 = nt * TC_BN;
             int bn = g.N - n0;
             bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
-            const int m_own = mt * TC_BM + q * 32 + lane;     // accumulator row owned in the TMEM-read phase
+            int m_own = mt * TC_BM + q * 32 + lane;           // accumulator row owned in the TMEM-read phase
             // rows this lane copies out: (lane >> 2) + 8*i of the warp's 32 rows
             int64_t obase[4];
             int64_t obase_own = -1;
-            if (L.out_mode == OUT_FINAL) {
+            if (L.tma) {
+                // box order: row r of the tile = (sample r >> box_shift, y (r >> bw_log2) & (bh - 1), x r & (bw - 1))
+                int rr = mt;
+                const int xt = rr % L.x_tiles;
+                rr /= L.x_tiles;
+                const int yt = rr % L.y_tiles, bt = rr / L.y_tiles;
+                const int bw_mask = (1 << L.bw_log2) - 1, bh_mask = (1 << L.bh_log2) - 1;
+                auto locate = [&](int r, RowIter& it) {
+                    it.b = (unsigned)(bt * nb_box + (r >> box_shift));
+                    it.oy = (unsigned)((yt << L.bh_log2) + ((r >> L.bw_log2) & bh_mask));
+                    it.ox = (unsigned)((xt << L.bw_log2) + (r & bw_mask));
+                    return (int)it.b < n_samples;
+                };
+                RowIter it;
+                m_own = locate(q * 32 + lane, it) ? (int)(it.b * (unsigned)g.P + it.oy * (unsigned)g.OW + it.ox) : L.M;
+                if (L.out_mode == OUT_FINAL && m_own < L.M) obase_own = out_offset(g, it);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) obase[i] = locate(q * 32 + (lane >> 2) + 8 * i, it) ? out_offset(g, it) : -1;
+            } else if (L.out_mode == OUT_FINAL) {
                 if (m_own < L.M) obase_own = out_offset(g, row_init(rs1, (unsigned)m_own));
             } else {
                 RowIter it = row_init(rs8, (unsigned)(mt * TC_BM + q * 32 + (lane >> 2)));
@@ -531,20 +598,87 @@ cudaError_t gemm_tc_init() {
 }
 
 static int g_num_sms = 0;
+static int g_tma_enabled = -1;
 
-int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream) {
-    if (L.M == 0) return 0;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+void gemm_tc_set_tma(int enabled) { g_tma_enabled = enabled ? 1 : 0; }
+
+static int log2_pow2_divisor(int v, int cap) {   // log2 of the largest power of two dividing v, not above cap
+    int l = 0;
+    while ((v & 1) == 0 && (2 << l) <= cap) {
+        v >>= 1;
+        ++l;
+    }
+    return l;
+}
+
+// NHWC activation plane [n, IH, IW, Cin] as a rank-4 tensor map with a (64 channels, bw pixels, bh pixels, nb samples) box
+static bool make_act_map(CUtensorMap* map, const void* base, const GemmGeom& g, int n, int bw, int bh, int nb) {
+    const cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.IW * g.Cin * 2, (cuuint64_t)g.in_sample_stride * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)(bw * g.sx_o), (cuuint32_t)(bh * g.sy_o), (cuuint32_t)nb};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)g.sx_o, (cuuint32_t)g.sy_o, 1};
+    return g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
+    if (L_in.M == 0) return 0;
     if (g_num_sms == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = 148;
     }
-    const int num_nt = (L.g.N + TC_BN - 1) / TC_BN;
-    const int num_mt = (L.M + TC_BM - 1) / TC_BM;
+    if (g_tma_enabled < 0) {
+        const char* e = getenv("PNN_TMA");          // default on; PNN_TMA=0 selects the cp.async gather for every layer
+        g_tma_enabled = e ? atoi(e) != 0 : 1;
+    }
+    GemmLaunch L = L_in;
+    const GemmGeom& g = L.g;
+    alignas(64) CUtensorMap map_hi, map_lo;
+    memset(&map_hi, 0, sizeof(map_hi));
+    memset(&map_lo, 0, sizeof(map_lo));
+    L.tma = 0;
+    // real convolutions with 64-channel K blocks, forward stride (tconv phases walk taps backwards with sx_o = 1: fine)
+    if (g_tma_enabled && g.TH * g.TW > 1 && g.Cin % 64 == 0 && g.sx_o >= 1 && g.sy_o >= 1 && g.sx_o <= 2 && g.sy_o <= 2 &&
+        g.P == (g.P / g.OW) * g.OW && L.M % g.P == 0) {
+        if (!g_encode_tiled) {
+            cudaDriverEntryPointQueryResult qres;
+            void* fn = nullptr;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+                qres == cudaDriverEntryPointSuccess) {
+                g_encode_tiled = (EncodeTiledFn)fn;
+            }
+        }
+        const int OH = g.P / g.OW;
+        const int bwl = log2_pow2_divisor(g.OW, TC_BM);
+        const int bhl = log2_pow2_divisor(OH, TC_BM >> bwl);
+        const int bw = 1 << bwl, bh = 1 << bhl, nb = TC_BM / (bw * bh);
+        const int n = L.M / g.P;
+        if (g_encode_tiled && bw * g.sx_o <= 256 && bh * g.sy_o <= 256 && make_act_map(&map_hi, L.in.p0, g, n, bw, bh, nb) &&
+            make_act_map(&map_lo, L.in.p1, g, n, bw, bh, nb)) {
+            L.tma = 1;
+            L.bw_log2 = bwl;
+            L.bh_log2 = bhl;
+            L.x_tiles = g.OW / bw;
+            L.y_tiles = OH / bh;
+        }
+    }
+    const int num_nt = (g.N + TC_BN - 1) / TC_BN;
+    long long num_mt = (L.M + TC_BM - 1) / TC_BM;
+    if (L.tma) {
+        const int nb = TC_BM >> (L.bw_log2 + L.bh_log2);
+        num_mt = (long long)((L.M / g.P + nb - 1) / nb) * L.y_tiles * L.x_tiles;
+    }
     const long long tiles = (long long)num_nt * num_mt * (L.split_k > 1 ? L.split_k : 1);
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);   // persistent: one CTA per SM
-    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(L);
+    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(L, map_hi, map_lo);
     return 1;
 }
 

@@ -68,6 +68,11 @@ struct GemmLaunch {
     // bias / LeakyReLU / hi-lo split.  1 = off.
     int split_k;
     float* partial;
+    // TMA path for the A operand of real convolutions (Cin % 64 == 0, more than one tap): the M tile is a box of
+    // bw x bh output pixels x nb samples (bw * bh * nb = 128, powers of two) loaded by ONE cp.async.bulk.tensor per
+    // plane and K block (hardware 128B swizzle, zero fill for SAME padding, element strides for stride 2).
+    int tma;                    // 1: tile = (sample tile, y tile, x tile, n tile), rows in box order
+    int bw_log2, bh_log2, x_tiles, y_tiles;
 };
 int launch_splitk_reduce(const GemmLaunch& L, cudaStream_t stream);
 
@@ -99,7 +104,8 @@ inline size_t tc_total_bytes(int N, int K) { return tc_tile_offset(N, K, tc_num_
 // Each returns the number of kernels it launched.
 // ---------------------------------------------------------------------------------------------
 int launch_gemm_fp32(const GemmLaunch& L, cudaStream_t stream);
-int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);
+int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);   // fills the TMA fields itself when the path applies
+void gemm_tc_set_tma(int enabled);
 // one-time opt-in for the tcgen05 kernel's dynamic shared memory
 cudaError_t gemm_tc_init();
 
