@@ -15,7 +15,7 @@ EXPORTS = (
     'pnn_set_context', 'pnn_predict_hm', 'pnn_predict_batch', 'pnn_predict_image_blocks',
     'pnn_predict_batch_device', 'pnn_predict_image_blocks_device', 'pnn_launch_count',
     'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation', 'pnn_win_flags_device', 'pnn_set_profiling',
-    'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused',
+    'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused', 'pnn_hevc_best_mode', 'pnn_hevc_best_mode_device',
 )
 
 PRECISION_FP32 = 0
@@ -76,6 +76,10 @@ def load():
     lib.pnn_predict_hm_context.restype = i32
     lib.pnn_set_hm_fused.argtypes = [vp, i32]
     lib.pnn_set_hm_fused.restype = i32
+    lib.pnn_hevc_best_mode.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.pnn_hevc_best_mode.restype = i32
+    lib.pnn_hevc_best_mode_device.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
+    lib.pnn_hevc_best_mode_device.restype = i32
     lib.pnn_version.argtypes = []
     lib.pnn_version.restype = c.c_char_p
     _lib = lib

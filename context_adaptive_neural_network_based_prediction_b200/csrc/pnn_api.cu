@@ -911,6 +911,77 @@ int pnn_debug_get_activation(pnn_handle* h, int width, int is_fc, int buffer_ind
     return 0;
 }
 
+int pnn_hevc_best_mode_device(pnn_handle* h, int width, const uint8_t* d_images, int n_images, int height, int width_image,
+                              const int32_t* d_idx, const int32_t* d_rows, const int32_t* d_cols, int64_t n, int mask_w,
+                              int mask_h, uint8_t* d_best, double* d_psnr, uint8_t* d_pred, void* stream) {
+    if (!h) return -1;
+    try {
+        if (n < 0) throw std::runtime_error("negative number of blocks");
+        if (width != 4 && width != 8 && width != 16 && width != 32 && width != 64) {
+            throw std::runtime_error("the width of the target patch does not belong to {4, 8, 16, 32, 64}");
+        }
+        if (!d_images || !d_rows || !d_cols) throw std::runtime_error("NULL buffer");
+        if (n_images > 1 && !d_idx) throw std::runtime_error("`image_index` is NULL while there are several images");
+        check_masks(width, mask_w, mask_h);                       // intraprediction.py:66-72
+        CUDA_TRY(cudaSetDevice(h->device));
+        ProfScope ps(h, (cudaStream_t)stream, "hevc_best_mode", n, 35, (int64_t)width * width, false);
+        h->launches += launch_hevc_best_mode(d_images, d_idx, d_rows, d_cols, n, height, width_image, width, mask_w, mask_h,
+                                             d_best, d_psnr, d_pred, (cudaStream_t)stream);
+        CUDA_TRY(cudaGetLastError());
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_hevc_best_mode(pnn_handle* h, int width, const uint8_t* images, int n_images, int height, int width_image,
+                       const int32_t* idx, const int32_t* rows, const int32_t* cols, int64_t n, int mask_w, int mask_h,
+                       uint8_t* best, double* psnr, uint8_t* pred) {
+    if (!h) return -1;
+    try {
+        if (n < 0) throw std::runtime_error("negative number of blocks");
+        if (!images || !rows || !cols) throw std::runtime_error("NULL buffer");
+        if (n_images <= 0 || height <= 0 || width_image <= 0) throw std::runtime_error("empty image set");
+        if (n_images > 1 && !idx) throw std::runtime_error("`image_index` is NULL while there are several images");
+        for (int64_t i = 0; i < n; ++i) {
+            // the block and the first pixel of its intra pattern must lie inside the image
+            if (rows[i] < 1 || cols[i] < 1 || rows[i] + width > height || cols[i] + width > width_image) {
+                throw std::runtime_error("block " + std::to_string(i) + " or its intra pattern anchor lies outside the image");
+            }
+            if (idx && (idx[i] < 0 || idx[i] >= n_images)) throw std::runtime_error("`image_index` out of range");
+        }
+        if (n == 0) return 0;
+        CUDA_TRY(cudaSetDevice(h->device));
+        cudaStream_t s = h->stream;
+        const size_t img_bytes = (size_t)n_images * height * width_image, px = (size_t)width * width;
+        h->d_images.reserve(img_bytes);
+        h->d_rows.reserve(n * 4);
+        h->d_cols.reserve(n * 4);
+        if (idx) h->d_idx.reserve(n * 4);
+        h->d_in0.reserve((size_t)n * (px + 1));
+        h->d_in1.reserve((size_t)n * 8);
+        CUDA_TRY(cudaMemcpyAsync(h->d_images.p, images, img_bytes, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->d_rows.p, rows, n * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->d_cols.p, cols, n * 4, cudaMemcpyHostToDevice, s));
+        if (idx) CUDA_TRY(cudaMemcpyAsync(h->d_idx.p, idx, n * 4, cudaMemcpyHostToDevice, s));
+        uint8_t* d_pred = (uint8_t*)h->d_in0.p;
+        uint8_t* d_best = d_pred + (size_t)n * px;
+        if (pnn_hevc_best_mode_device(h, width, (const uint8_t*)h->d_images.p, n_images, height, width_image,
+                                      idx ? (const int32_t*)h->d_idx.p : nullptr, (const int32_t*)h->d_rows.p,
+                                      (const int32_t*)h->d_cols.p, n, mask_w, mask_h, best ? d_best : nullptr,
+                                      psnr ? (double*)h->d_in1.p : nullptr, pred ? d_pred : nullptr, s) != 0) {
+            return -1;
+        }
+        if (best) CUDA_TRY(cudaMemcpyAsync(best, d_best, n, cudaMemcpyDeviceToHost, s));
+        if (psnr) CUDA_TRY(cudaMemcpyAsync(psnr, h->d_in1.p, n * 8, cudaMemcpyDeviceToHost, s));
+        if (pred) CUDA_TRY(cudaMemcpyAsync(pred, d_pred, (size_t)n * px, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
 int pnn_win_flags_device(pnn_handle* h, const double* d_psnr, const double* d_base, int64_t n, uint8_t* d_win, void* stream) {
     if (!h) return -1;
     try {

@@ -210,6 +210,11 @@ constexpr int FC_CHAIN_CTAS = 75;    // 1200 hidden units / 16 columns per CTA
 int launch_fc_chain(const FcChainLaunch& L, cudaStream_t stream);
 void small_kernels_init();
 
+// Best HEVC intra mode of every block (35 modes on an unfiltered pattern) -- the baseline of the offline evaluation.
+int launch_hevc_best_mode(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols, int64_t n,
+                          int H, int Wimg, int W, int mask_w, int mask_h, uint8_t* best_index, double* psnr, uint8_t* pred,
+                          cudaStream_t stream);
+
 int launch_win_flags(const double* psnr, const double* baseline, int64_t n, uint8_t* win, cudaStream_t stream);
 
 // fp32 -> (fp32 copy | split planes)

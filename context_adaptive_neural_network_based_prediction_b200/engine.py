@@ -155,6 +155,36 @@ class Engine(object):
             out['psnrs'] = psnr
         return out
 
+    def hevc_best_mode(self, width_target, images_uint8, rows, cols, image_index=None, masks=(0, 0), want_predictions=True):
+        """Best of the 35 HEVC intra modes per block (reference hevc/intraprediction/intraprediction.py:183-292).
+
+        Returns a dict with 'indices_hevc_best_mode' uint8 [N], 'psnrs_hevc_best_mode' float64 [N] and, if requested,
+        'predictions_hevc_best_mode_uint8' [N, W, W].
+        """
+        img = numpy.ascontiguousarray(images_uint8, dtype=numpy.uint8)
+        if img.ndim == 2:
+            img = img[None]
+        rows = numpy.ascontiguousarray(rows, dtype=numpy.int32)
+        cols = numpy.ascontiguousarray(cols, dtype=numpy.int32)
+        idx = None if image_index is None else numpy.ascontiguousarray(image_index, dtype=numpy.int32)
+        n, w = rows.shape[0], width_target
+        best = numpy.empty(n, dtype=numpy.uint8)
+        psnr = numpy.empty(n, dtype=numpy.float64)
+        pred = numpy.empty((n, w, w), dtype=numpy.uint8) if want_predictions else None
+        self._check(self._lib.pnn_hevc_best_mode(self._h, w, _ptr(img), img.shape[0], img.shape[1], img.shape[2], _ptr(idx),
+                                                 _ptr(rows), _ptr(cols), n, int(masks[0]), int(masks[1]), _ptr(best), _ptr(psnr),
+                                                 _ptr(pred)))
+        out = {'indices_hevc_best_mode': best, 'psnrs_hevc_best_mode': psnr}
+        if want_predictions:
+            out['predictions_hevc_best_mode_uint8'] = pred
+        return out
+
+    def hevc_best_mode_device(self, width_target, d_images, n_images, height, width_image, d_image_index, d_rows, d_cols, n,
+                              masks, d_best_index, d_psnr, d_pred_u8, stream=0):
+        self._check(self._lib.pnn_hevc_best_mode_device(self._h, width_target, d_images, n_images, height, width_image,
+                                                        d_image_index, d_rows, d_cols, n, int(masks[0]), int(masks[1]),
+                                                        d_best_index, d_psnr, d_pred_u8, stream))
+
     # ------------------------------------------------------------------ offline path, device buffers
     def predict_image_blocks_device(self, width_target, is_fully_connected, d_images, n_images, height, width_image,
                                     d_image_index, d_rows, d_cols, n, masks, d_out_f32, d_out_u8, d_out_psnr,

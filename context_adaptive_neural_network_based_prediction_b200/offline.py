@@ -31,6 +31,26 @@ def blocks_of_images(nb_images, height, width_image, width_target):
     return idx, numpy.tile(rows, nb_images), numpy.tile(cols, nb_images)
 
 
+def evaluate_blocks(engine, images_uint8, width_target, is_fully_connected, rows, cols, image_index=None, masks=(0, 0)):
+    """PNN versus the best HEVC intra mode on the given blocks: the body of the reference's `predict_mask`
+    (comparing_pnn_ipfcns_hevc_best_mode.py:220-322) in two library calls, with the reference's dictionary keys."""
+    pnn = engine.predict_image_blocks(width_target, is_fully_connected, images_uint8, rows, cols, image_index, masks=masks,
+                                      want_float=False)
+    hevc = engine.hevc_best_mode(width_target, images_uint8, rows, cols, image_index, masks=masks, want_predictions=False)
+    psnrs_pnn, psnrs_hevc = pnn['psnrs'], hevc['psnrs_hevc_best_mode']
+    n = max(1, len(psnrs_pnn))
+    return {
+        'psnrs_pnn': psnrs_pnn,
+        'indices_hevc_best_mode': hevc['indices_hevc_best_mode'],
+        'psnrs_hevc_best_mode': psnrs_hevc,
+        'mean_psnr_pnn': float(numpy.mean(psnrs_pnn)) if len(psnrs_pnn) else float('nan'),
+        'mean_psnr_hevc_best_mode': float(numpy.mean(psnrs_hevc)) if len(psnrs_hevc) else float('nan'),
+        # comparing_pnn_ipfcns_hevc_best_mode.py:87
+        'frequency_win_pnn': float(numpy.count_nonzero(psnrs_pnn - psnrs_hevc > 0.)) / n,
+        'predictions_pnn_uint8': pnn['predictions_uint8'],
+    }
+
+
 def gather_statistics(psnrs_local, wins_local, rank, world_size, group=None):
     """ONE gather of the per-block statistics to rank 0.
 

@@ -148,6 +148,24 @@ int64_t pnn_launch_count(pnn_handle* h);
 float pnn_last_hm_device_ms(pnn_handle* h);
 
 /*
+ * Baseline of the offline evaluation: the best of the 35 HEVC intra prediction modes for every block, replacing
+ * extract_intra_patterns + predict_series_via_hevc_best_mode (hevc/intraprediction/intraprediction.py:8-292, which loops
+ * over hevc_intraprediction, hevc/intraprediction/c++/source/extracted_hevc_intraprediction.cpp:3-421, through Cython).
+ * Blocks are addressed like in pnn_predict_image_blocks; the intra pattern starts at (row - 1, col - 1)
+ * (comparing_pnn_ipfcns_hevc_best_mode.py:234-235), is 2W + 1 - mask_h high and 2W + 1 - mask_w wide, and its missing
+ * part (masked or outside the image) is padded with the last pixel as the reference does.  Integer arithmetic, bit-exact.
+ * Outputs (each may be NULL): best_index[n] (first mode with the highest PSNR), psnr[n] float64, pred_u8 [n, W*W].
+ * The first variant takes HOST pointers, the second DEVICE pointers (asynchronous on `cuda_stream`).
+ */
+int pnn_hevc_best_mode(pnn_handle* h, int width, const uint8_t* images, int n_images, int height, int width_image,
+                       const int32_t* image_index, const int32_t* rows, const int32_t* cols, int64_t n, int mask_w, int mask_h,
+                       uint8_t* best_index, double* psnr, uint8_t* pred_u8);
+int pnn_hevc_best_mode_device(pnn_handle* h, int width, const uint8_t* d_images, int n_images, int height, int width_image,
+                              const int32_t* d_image_index, const int32_t* d_rows, const int32_t* d_cols, int64_t n,
+                              int mask_w, int mask_h, uint8_t* d_best_index, double* d_psnr, uint8_t* d_pred_u8,
+                              void* cuda_stream);
+
+/*
  * Win flags of the offline evaluation (reference comparing_pnn_ipfcns_hevc_best_mode.py:87):
  * d_win[i] = (d_psnr[i] - d_psnr_baseline[i] > 0).  DEVICE pointers, asynchronous on `cuda_stream`.
  */

@@ -17,6 +17,9 @@ Fixtures:
   extract_ref.npz
       inputs and outputs of the reference's own extract_context_portions (compiled unmodified into
       oracle/_ref/libextract_ref.so) on random planes and random availability patterns.
+  hevc_ref.npz
+      intra patterns and the 35 predictions of the reference's own hevc_intraprediction (compiled unmodified into
+      oracle/_ref/libhevc_intra_ref.so) for widths 4 .. 64, with and without masks.
 """
 import ctypes
 import os
@@ -112,6 +115,32 @@ def main():
     cases['n_cases'] = numpy.array([idx], dtype=numpy.int32)
     numpy.savez_compressed(os.path.join(HERE, 'extract_ref.npz'), **cases)
     print('wrote %d extraction cases' % idx)
+
+    # reference hevc_intraprediction, compiled unmodified (oracle/Makefile target `ref`)
+    lib = ctypes.CDLL(os.path.join(ROOT, 'oracle/_ref/libhevc_intra_ref.so'))
+    hevc = {}
+    idx = 0
+    for width, n_patterns in ((4, 3), (8, 3), (16, 2), (32, 1), (64, 1)):
+        for trial in range(n_patterns):
+            mask_w = 0 if trial == 0 else 4 * int(rng.integers(0, width // 4 + 1))
+            mask_h = 0 if trial == 0 else 4 * int(rng.integers(0, width // 4 + 1))
+            hp, wp = 2 * width + 1 - mask_h, 2 * width + 1 - mask_w
+            yy, xx = numpy.mgrid[0:hp, 0:wp]
+            pattern = numpy.clip(110 + 3 * xx - 2 * yy + rng.integers(-12, 13, (hp, wp)), 0, 255).astype(numpy.uint8)
+            preds = numpy.zeros((35, width, width), dtype=numpy.uint8)
+            for mode in range(35):
+                out = numpy.zeros(width * width, dtype=numpy.uint8)
+                assert lib.ref_hevc_intraprediction(hp, wp, width, pattern.ctypes.data_as(ctypes.c_void_p),
+                                                    out.ctypes.data_as(ctypes.c_void_p), mode) == 0
+                preds[mode] = out.reshape(width, width)
+            hevc['h%d_row' % idx] = pattern[0].copy()
+            hevc['h%d_col' % idx] = pattern[:, 0].copy()
+            hevc['h%d_width' % idx] = numpy.array([width], dtype=numpy.int32)
+            hevc['h%d_preds' % idx] = preds
+            idx += 1
+    hevc['n_cases'] = numpy.array([idx], dtype=numpy.int32)
+    numpy.savez_compressed(os.path.join(HERE, 'hevc_ref.npz'), **hevc)
+    print('wrote %d HEVC intra cases' % idx)
 
 
 if __name__ == '__main__':
