@@ -96,20 +96,19 @@ def test_gpu_best_mode_errors(engine):
 def test_offline_evaluation_keys_and_win_rate(engine, golden_dir):
     """offline.evaluate_blocks = the reference's predict_mask body; checked with a trained checkpoint on a real image."""
     from context_adaptive_neural_network_based_prediction_b200 import offline, weights as W
-    from oracle import context, nets
     width = 8
     path = os.path.join(golden_dir, 'conv8_single.pnnw')
     engine.load_net(path)
     _, _, wts = W.load_flat(path)
     img = numpy.load(os.path.join(golden_dir, 'cliff_luma.npy'))
     rows, cols = helpers.grid_blocks(img.shape[0], img.shape[1], width)
-    got = offline.evaluate_blocks(engine, img, width, False, rows, cols)
-    above, left, _, targets = context.gather_image_blocks(img[None], numpy.zeros(len(rows), int), rows, cols, width, helpers.MEAN, 0, 0)
-    pred_u8 = epilogue.epilogue_numpy(nets.forward_conv(wts, above, left)[..., 0], helpers.MEAN)
-    _, psnrs_hevc, _ = hevc_intra.best_modes_of_blocks(img[None], numpy.zeros(len(rows), int), rows, cols, width, 0, 0)
-    psnrs_pnn, freq = epilogue.performance_vs_baseline(targets, pred_u8, psnrs_hevc)
+    idx = numpy.zeros(len(rows), dtype=numpy.int64)
+    got = offline.evaluate_blocks(engine, img[None], width, False, rows, cols)
+    _, pred_u8, psnrs_pnn, _ = helpers.oracle_predict_blocks(wts, width, False, img[None], idx, rows, cols)
+    _, psnrs_hevc, _ = hevc_intra.best_modes_of_blocks(img[None], idx, rows, cols, width, 0, 0)
+    freq = float(numpy.count_nonzero(psnrs_pnn - psnrs_hevc > 0.)) / len(rows)
     numpy.testing.assert_allclose(got['psnrs_hevc_best_mode'], psnrs_hevc, rtol=0, atol=1e-9)
-    same = (got['predictions_pnn_uint8'] == pred_u8).reshape(len(rows), -1).all(axis=1)
+    same = (got['predictions_pnn_uint8'].reshape(len(rows), -1) == pred_u8.reshape(len(rows), -1)).all(axis=1)
     assert same.mean() > 0.99
     numpy.testing.assert_allclose(got['psnrs_pnn'][same], psnrs_pnn[same], rtol=0, atol=1e-9)
     assert abs(got['frequency_win_pnn'] - freq) <= (1. - same.mean()) + 1e-12
