@@ -16,6 +16,7 @@ EXPORTS = (
     'pnn_predict_batch_device', 'pnn_predict_image_blocks_device', 'pnn_launch_count',
     'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation', 'pnn_win_flags_device', 'pnn_set_profiling',
     'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused', 'pnn_hevc_best_mode', 'pnn_hevc_best_mode_device',
+    'pnn_inspect_net_file',
 )
 
 PRECISION_FP32 = 0
@@ -43,6 +44,9 @@ def load():
     lib.pnn_last_error.restype = c.c_char_p
     lib.pnn_load_net.argtypes = [vp, c.c_char_p]
     lib.pnn_load_net.restype = i32
+    lib.pnn_inspect_net_file.argtypes = [c.c_char_p, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int64),
+                                         c.POINTER(c.c_double)]
+    lib.pnn_inspect_net_file.restype = i32
     lib.pnn_set_precision.argtypes = [vp, i32]
     lib.pnn_set_precision.restype = i32
     lib.pnn_set_context.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32]

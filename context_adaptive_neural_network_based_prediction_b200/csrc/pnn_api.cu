@@ -127,19 +127,19 @@ struct Net {
     ~Net() { drop_hm_graph(); }
 };
 
-struct FlatFile {
-    int width = 0;
-    bool is_fc = false;
-    std::map<std::string, std::vector<float>> t;
-    std::map<std::string, std::vector<int>> shape;
-};
-
 FlatFile read_flat(const std::string& path) {
     std::ifstream f(path, std::ios::binary);
     if (!f) throw std::runtime_error("cannot open weights file \"" + path + "\"");
     std::vector<char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     if (data.size() < 24 || memcmp(data.data(), "PNNWv001", 8) != 0) {
-        throw std::runtime_error("\"" + path + "\" is not a PNNW flat binary");
+        // not our flat binary: the frozen graph the reference's HM loads (load_graph, integration_...cpp:29-69)?
+        FlatFile graph;
+        try {
+            read_frozen_graph(data, path, &graph);
+        } catch (const std::exception& e) {
+            throw std::runtime_error("\"" + path + "\" is neither a PNNW flat binary nor a frozen PNN graph (" + e.what() + ")");
+        }
+        return graph;
     }
     auto u32 = [&](size_t pos) {
         if (pos + 4 > data.size()) throw std::runtime_error("truncated weights file \"" + path + "\"");
@@ -842,6 +842,30 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
     }
     *out = h.release();
     return 0;
+}
+
+int pnn_inspect_net_file(const char* path, int* width_target, int* is_fully_connected, int64_t* n_parameters,
+                         double* checksum) {
+    try {
+        if (!path) throw std::runtime_error("`path` is NULL");
+        const FlatFile ff = read_flat(path);
+        int64_t n = 0;
+        double sum = 0.;
+        for (const auto& kv : ff.t) {
+            double s = 0.;
+            for (size_t i = 0; i < kv.second.size(); ++i) s += (double)(i % 7 + 1) * (double)kv.second[i];
+            sum += s;
+            n += (int64_t)kv.second.size();
+        }
+        if (width_target) *width_target = ff.width;
+        if (is_fully_connected) *is_fully_connected = ff.is_fc ? 1 : 0;
+        if (n_parameters) *n_parameters = n;
+        if (checksum) *checksum = sum;
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return -1;
+    }
 }
 
 void pnn_destroy(pnn_handle* h) {

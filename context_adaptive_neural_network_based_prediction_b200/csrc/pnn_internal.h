@@ -224,4 +224,16 @@ int launch_convert_input(const float* src, Act dst, int64_t n_elems, int split, 
 int launch_psnr(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols,
                 int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream);
 
+// ---------------------------------------------------------------- weight files (host side)
+// Tensors of one net keyed by the TensorFlow variable names of the reference graph (reference layouts).
+struct FlatFile {
+    int width = 0;
+    bool is_fc = false;
+    std::map<std::string, std::vector<float>> t;
+    std::map<std::string, std::vector<int>> shape;
+};
+// Binary GraphDef written by the reference's freezing script (`graph_output.pbtxt`, freezing_graph_pnn.py:129-139):
+// fills `out` from its float `Const` nodes and infers width / kind from their names and shapes.  Throws on malformed input.
+void read_frozen_graph(const std::vector<char>& data, const std::string& path, FlatFile* out);
+
 }  // namespace pnn

@@ -16,6 +16,16 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def inspect_net_file(path):
+    """Host-only: (width_target, is_fully_connected, n_parameters, checksum) of a PNNW file or a frozen graph, parsed
+    by the library exactly as `Engine.load_net` parses it (C ABI pnn_inspect_net_file).  Needs no GPU."""
+    lib = _lib.load()
+    w, fc, n, cs = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_double()
+    if lib.pnn_inspect_net_file(path.encode(), ctypes.byref(w), ctypes.byref(fc), ctypes.byref(n), ctypes.byref(cs)) != 0:
+        raise PnnError(lib.pnn_last_error(None).decode())
+    return w.value, bool(fc.value), n.value, cs.value
+
+
 class Engine(object):
     """One `pnn_handle`: the nets loaded on one GPU.
 

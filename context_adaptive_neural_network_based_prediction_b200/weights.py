@@ -259,3 +259,150 @@ def export_checkpoint(prefix, width_target, is_fully_connected, path_out):
     weights = {n: variables[n] for n in tensor_shapes(width_target, is_fully_connected)}
     save_flat(path_out, width_target, is_fully_connected, weights)
     return weights
+
+
+# ----------------------------------------------------------------------------
+# Frozen-graph reader (binary GraphDef written by reference freezing_graph_pnn.py:129-139; no TensorFlow needed)
+# ----------------------------------------------------------------------------
+
+def _proto_fields(buf):
+    """(field number, wire type, value) of one serialized protobuf message; length-delimited values are memoryviews."""
+    pos, n = 0, len(buf)
+    while pos < n:
+        tag, pos = _varint(buf, pos)
+        field, wire = tag >> 3, tag & 7
+        if wire == 0:
+            value, pos = _varint(buf, pos)
+        elif wire == 1:
+            value, pos = buf[pos:pos + 8], pos + 8
+        elif wire == 2:
+            ln, pos = _varint(buf, pos)
+            value, pos = buf[pos:pos + ln], pos + ln
+        elif wire == 5:
+            value, pos = buf[pos:pos + 4], pos + 4
+        else:
+            raise ValueError('unsupported protobuf wire type %d' % wire)
+        if pos > n:
+            raise ValueError('truncated protobuf message')
+        yield field, wire, value
+
+
+def _parse_tensor_proto(buf):
+    """TensorProto: 1 dtype, 2 tensor_shape{2 dim{1 size}}, 4 tensor_content, 5 float_val.  float32 only (DT_FLOAT = 1)."""
+    dtype, dims, content, float_vals = 0, [], None, []
+    for field, wire, value in _proto_fields(buf):
+        if field == 1 and wire == 0:
+            dtype = value
+        elif field == 2 and wire == 2:
+            for f2, w2, dim in _proto_fields(value):
+                if f2 == 2 and w2 == 2:
+                    size = 0
+                    for f3, w3, v3 in _proto_fields(dim):
+                        if f3 == 1 and w3 == 0:
+                            size = v3
+                    dims.append(size)
+        elif field == 4 and wire == 2:
+            content = bytes(value)
+        elif field == 5:
+            if wire == 2:                                   # packed
+                float_vals.extend(numpy.frombuffer(bytes(value), dtype='<f4').tolist())
+            elif wire == 5:
+                float_vals.append(struct.unpack('<f', bytes(value))[0])
+    if dtype != 1:
+        return None
+    count = int(numpy.prod(dims)) if dims else 1
+    if content:
+        arr = numpy.frombuffer(content, dtype='<f4')
+        if arr.size != count:
+            raise ValueError('tensor_content holds %d floats, the shape %s needs %d' % (arr.size, dims, count))
+    elif len(float_vals) == count:
+        arr = numpy.asarray(float_vals, dtype=numpy.float32)
+    elif len(float_vals) == 1:                              # TensorFlow stores a constant-filled tensor as one value
+        arr = numpy.full(count, float_vals[0], dtype=numpy.float32)
+    elif not float_vals:
+        arr = numpy.zeros(count, dtype=numpy.float32)
+    else:
+        raise ValueError('float_val holds %d values for shape %s' % (len(float_vals), dims))
+    return arr.astype(numpy.float32).reshape(dims)
+
+
+def read_frozen_graph(path):
+    """{node name: float32 array} of the `Const` nodes of a frozen GraphDef, plus the list of (name, op) of all nodes.
+
+    `freeze_graph` (reference freezing_graph_pnn.py:129-139) turns every variable into a `Const` node carrying the
+    variable's name, so the keys are the names of `tensor_shapes`.  The file the reference calls `graph_output.pbtxt`
+    is a BINARY GraphDef despite its suffix; HM reads it with `ReadBinaryProto` (integration_...cpp:29-69).
+    """
+    with open(path, 'rb') as f:
+        data = f.read()
+    if data[:64].lstrip()[:4] in (b'node', b'vers', b'libr') or data[:1] == b'#':
+        raise ValueError('%s is a text-format GraphDef; the engine reads the binary file freeze_graph writes' % path)
+    consts, nodes = {}, []
+    view = memoryview(data)
+    for field, wire, node in _proto_fields(view):
+        if field != 1 or wire != 2:
+            continue                                        # versions, library
+        name, op, tensor = '', '', None
+        for f2, w2, v2 in _proto_fields(node):
+            if f2 == 1 and w2 == 2:
+                name = bytes(v2).decode()
+            elif f2 == 2 and w2 == 2:
+                op = bytes(v2).decode()
+            elif f2 == 5 and w2 == 2:                       # map<string, AttrValue> entry
+                key, attr = b'', None
+                for f3, w3, v3 in _proto_fields(v2):
+                    if f3 == 1 and w3 == 2:
+                        key = bytes(v3)
+                    elif f3 == 2 and w3 == 2:
+                        attr = v3
+                if key == b'value' and attr is not None:
+                    for f4, w4, v4 in _proto_fields(attr):
+                        if f4 == 8 and w4 == 2:             # AttrValue.tensor
+                            tensor = v4
+        nodes.append((name, op))
+        if op == 'Const' and tensor is not None:
+            arr = _parse_tensor_proto(tensor)
+            if arr is not None:
+                consts[name] = arr
+    return consts, nodes
+
+
+def export_frozen_graph(path_graph, width_target, is_fully_connected, path_out):
+    """Frozen graph (`graph_output.pbtxt` of the reference's HM set-up) -> flat binary."""
+    consts, _ = read_frozen_graph(path_graph)
+    shapes = tensor_shapes(width_target, is_fully_connected)
+    missing = [n for n in shapes if n not in consts]
+    if missing:
+        raise ValueError('%s holds no constant named %s (is it the graph of width %d, %s?)'
+                         % (path_graph, missing[0], width_target, 'fully-connected' if is_fully_connected else 'convolutional'))
+    weights = {}
+    for n, shape in shapes.items():
+        if tuple(consts[n].shape) != tuple(shape):
+            raise ValueError('%s: shape %s, expected %s' % (n, consts[n].shape, shape))
+        weights[n] = consts[n]
+    save_flat(path_out, width_target, is_fully_connected, weights)
+    return weights
+
+
+def main(argv=None):
+    """python -m <pkg>.weights (--checkpoint PREFIX | --frozen-graph FILE) --width W (--fc | --conv) --out FILE.pnnw"""
+    import argparse
+    ap = argparse.ArgumentParser(description='export the weights of one PNN to the flat binary libpnn_cuda loads')
+    src = ap.add_mutually_exclusive_group(required=True)
+    src.add_argument('--checkpoint', help='TensorFlow V2 checkpoint prefix, e.g. .../model_800000.ckpt')
+    src.add_argument('--frozen-graph', help='binary GraphDef written by freezing_graph_pnn.py (graph_output.pbtxt)')
+    ap.add_argument('--width', type=int, required=True, choices=(4, 8, 16, 32, 64))
+    kind = ap.add_mutually_exclusive_group(required=True)
+    kind.add_argument('--fc', action='store_true')
+    kind.add_argument('--conv', action='store_true')
+    ap.add_argument('--out', required=True)
+    a = ap.parse_args(argv)
+    if a.checkpoint:
+        w = export_checkpoint(a.checkpoint, a.width, a.fc, a.out)
+    else:
+        w = export_frozen_graph(a.frozen_graph, a.width, a.fc, a.out)
+    print('%s: %d tensors, %d parameters' % (a.out, len(w), sum(v.size for v in w.values())))
+
+
+if __name__ == '__main__':
+    main()

@@ -108,23 +108,21 @@ void create_tensors_flattened_context(std::vector<tensorflow::Tensor>& tensors_f
     }
 }
 
-// reference integration_prediction_neural_network.cpp:29-54: one frozen graph -> one session.  Here the path
-// names a PNNW flat binary; a path ending in ".pbtxt" is mapped to its ".pnnw" sibling.
+// reference integration_prediction_neural_network.cpp:29-54: one frozen graph -> one session.  The path may name
+// the frozen graph itself (the binary GraphDef `graph_output.pbtxt`; libpnn_cuda reads its constants) or a PNNW flat
+// binary; when a ".pnnw" sibling of a ".pbtxt" path exists it is preferred (faster to parse).
 tensorflow::Status load_graph(const tensorflow::string& path_to_graph_output,
                               std::unique_ptr<tensorflow::Session>& unique_ptr_session) {
     std::string path(path_to_graph_output);
     const std::string suffix(".pbtxt");
     if (path.size() > suffix.size() && path.compare(path.size() - suffix.size(), suffix.size(), suffix) == 0) {
-        path = path.substr(0, path.size() - suffix.size()) + ".pnnw";
+        const std::string sibling(path.substr(0, path.size() - suffix.size()) + ".pnnw");
+        if (std::ifstream(sibling.c_str(), std::ios::binary).good()) path = sibling;
     }
-    std::ifstream file(path.c_str(), std::ios::binary);
-    char header[16];
-    if (!file.read(header, 16) || memcmp(header, "PNNWv001", 8) != 0) {
-        return tensorflow::Status("Failed to load the weights at \"" + path + "\".");
+    int width(0), is_fc(0);
+    if (pnn_inspect_net_file(path.c_str(), &width, &is_fc, NULL, NULL) != 0) {
+        return tensorflow::Status("Failed to load the weights at \"" + path + "\": " + pnn_last_error(NULL));
     }
-    uint32_t width(0), is_fc(0);
-    memcpy(&width, header + 8, 4);
-    memcpy(&is_fc, header + 12, 4);
     pnn_handle* h(handle());
     if (!h) return tensorflow::Status("libpnn_cuda could not be initialised");
     if (pnn_load_net(h, path.c_str()) != 0) return tensorflow::Status(pnn_last_error(h));

@@ -42,7 +42,7 @@ enum {
  *
  * `paths_file` is the reference's "paths to graphs" file (lines `width,is_pair,0,path`, e.g.
  * hevc/hm_common/paths_to_graphs_output/pair.txt) whose paths now name PNNW flat binaries instead
- * of frozen .pbtxt graphs; it may be NULL, in which case nets are added with pnn_load_net.
+ * or, unchanged, the frozen graphs themselves (see pnn_load_net); it may be NULL, in which case nets are added with pnn_load_net.
  * `qp_selection` selects the "pair" models when it is >= 32 and the file lists pair entries
  * (TComPrediction.cpp:156); it must be > 0 (TComPrediction.cpp:129-133).
  * `mean_training` is the training-set mean (TComPrediction.cpp:219), `device` the CUDA ordinal.
@@ -56,11 +56,22 @@ void pnn_destroy(pnn_handle* h);
 const char* pnn_last_error(pnn_handle* h);
 
 /*
- * Loads one PNNW flat binary (width and type are read from its header) -- replaces one
- * load_graph call (integration_prediction_neural_network.cpp:29-54) /
- * PredictionNeuralNetwork.initialization (pnn/PredictionNeuralNetwork.py:185-200).
+ * Loads the weights of one net -- replaces one load_graph call
+ * (integration_prediction_neural_network.cpp:29-54) / PredictionNeuralNetwork.initialization
+ * (pnn/PredictionNeuralNetwork.py:185-200).  `path` names either a PNNW flat binary (width and type in
+ * its header) or the frozen graph the reference's HM loads (the binary GraphDef freezing_graph_pnn.py:129-139
+ * writes as `graph_output.pbtxt`): its float `Const` nodes carry the variable names, width and type are
+ * inferred from them.  No TensorFlow / protobuf library is involved.
  */
-int pnn_load_net(pnn_handle* h, const char* flat_binary_path);
+int pnn_load_net(pnn_handle* h, const char* path);
+
+/*
+ * Host-only (needs no GPU): parses a weights file exactly as pnn_load_net does and reports what it holds.
+ * `checksum` = sum over the tensors in name order of sum_i (i % 7 + 1) * value_i, in double.  Any output may be NULL.
+ * Returns 0, or -1 with the message in pnn_last_error(NULL).
+ */
+int pnn_inspect_net_file(const char* path, int* width_target, int* is_fully_connected, int64_t* n_parameters,
+                         double* checksum);
 
 /* PNN_PRECISION_*; default PNN_PRECISION_BF16X3. */
 int pnn_set_precision(pnn_handle* h, int precision);
