@@ -38,15 +38,33 @@ namespace pnn {
 
 namespace {
 
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 constexpr int A_PLANE = TC_BM * 128;                 // 16 KB
 constexpr int RING_BYTES = 2 * (2 * A_PLANE + 2 * TC_BN * 128);   // 192 KB: 2 stages at bn = 256, 3 at 128, 4 at <= 64
 constexpr int STAGING_BYTES = 8 * 4096;              // per epilogue warp: 32 rows x 64 B, hi and lo
-constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
+constexpr int XR_A_ROWS = 160;                       // tap-reuse box: (8 + 2) x bh x nb rows
+constexpr int XR_A_PLANE = XR_A_ROWS * 128;          // 20 KB
 constexpr int NUM_THREADS = 512;
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One lane of a converged warp.  The single-thread roles (TMA / bulk-copy producers, MMA issuer) run their whole loop
+// under this predicate: the compiler then knows exactly one thread is active and emits the uniform-datapath
+// instructions (UTCHMMA, UTMALDG, UBLKCP, UTCBAR) directly instead of an election loop with vector-to-uniform
+// register moves around every one of them, which made the issuer instruction-bound (~0.66 us per K block).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -90,6 +108,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t adesc_lo, ui
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
         "}" ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI)
+        : "memory");
+}
+// same with its own high word for the A descriptor (stride between 8-row groups other than 1024 bytes)
+__device__ __forceinline__ void umma_bf16_x(uint32_t tmem_d, uint32_t adesc_lo, uint32_t adesc_hi, uint32_t bdesc_lo, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %6};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(adesc_lo), "r"(bdesc_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI), "r"(adesc_hi)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
@@ -180,6 +212,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
     auto tmem_full = [&](int a) { return bars + 8u * (3 * MAX_STAGES + a); };
     auto tmem_empty = [&](int a) { return bars + 8u * (3 * MAX_STAGES + 2 + a); };
     const uint32_t tmem_slot = bars + 8u * (3 * MAX_STAGES + 4);
+    auto empty_a = [&](int s) { return bars + 8u * (3 * MAX_STAGES + 5 + s); };   // tap-reuse mode: A ring of its own
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_nt = (g.N + TC_BN - 1) / TC_BN;
@@ -203,12 +236,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
     // ONE MMA of width 2*bn whose two column halves (hi*hi and hi*lo) are added in the epilogue; with A_lo * B_hi that
     // makes 2 MMAs per K step instead of 3 and a third less A traffic from shared memory.
     const bool merged = g.N <= 128;
+    // tap-reuse mode: A ring (stages of two 20 KB planes) then B ring
+    // (the B ring must be deep: a K block of a narrow layer is ~0.35 us of tensor work against a ~2 us load round trip)
+    const int xr_na = 2, xr_nb = bn_max <= 32 ? 8 : (bn_max <= 64 ? 7 : 3);
+    const uint32_t xr_b_bytes = 2u * (uint32_t)bn_max * 128u;
+    const uint32_t xr_b_base = smem_base + (uint32_t)xr_na * 2u * XR_A_PLANE;
+    const int chunks = g.Cin >> 6;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < MAX_STAGES; ++s) {
             mbar_init(full_a(s), L.tma ? 1 : 128);
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
+            mbar_init(empty_a(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), 1);
@@ -227,9 +267,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp < 4 && L.tma) {
+    if (warp < 4 && L.xr) {
+        // ------------------------------------------------------------------ A producer, tap reuse: one box per (ty, chunk, group)
+        if (warp == 0 && elect_one()) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_hi) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_lo) : "memory");
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int r = tile / num_nt;
+                const int xt = r % L.x_tiles;
+                r /= L.x_tiles;
+                const int yt = r % L.y_tiles, bt = r / L.y_tiles;
+                const int ox0 = xt << L.bw_log2, oy0 = yt << L.bh_log2;
+                for (int ty = 0; ty < g.TH; ++ty) {
+                    const int c2 = oy0 * g.sy_o + ty * g.sy_t + g.cy;
+                    for (int ch = 0; ch < chunks; ++ch) {
+                        for (int xg = 0; xg < L.xr_groups; ++xg) {
+                            mbar_wait(empty_a(s), ph ^ 1u);
+                            const uint32_t a_hi = smem_base + (uint32_t)s * 2u * XR_A_PLANE;
+                            mbar_arrive_expect_tx(full_a(s), 2u * XR_A_PLANE);
+                            tma_load_4d(a_hi, &tmap_hi, ch * 64, ox0 * g.sx_o + L.xr_start[xg], c2, bt * nb_box, full_a(s));
+                            tma_load_4d(a_hi + XR_A_PLANE, &tmap_lo, ch * 64, ox0 * g.sx_o + L.xr_start[xg], c2, bt * nb_box, full_a(s));
+                            if (++s == xr_na) { s = 0; ph ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp < 4 && L.tma) {
         // ------------------------------------------------------------------ A producer, TMA: one thread, two box loads per K block
-        if (threadIdx.x == 0) {
+        if (warp == 0 && elect_one()) {
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_hi) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_lo) : "memory");
             int s = 0;
@@ -318,9 +386,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
                 if (++s == num_stages) { s = 0; ph ^= 1u; }
             }
         }
+    } else if (warp == 4 && L.xr) {
+        // ------------------------------------------------------------------ B producer, tap reuse: K blocks in (ty, chunk, group, tap) order
+        if (elect_one()) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nt = tile % num_nt;
+                int bn = g.N - nt * TC_BN;
+                bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
+                const uint32_t b_bytes = 2u * (uint32_t)bn * 128u;
+                const uint8_t* src = L.w_tiles + (size_t)nt * num_kb * (2u * TC_BN * 128u);
+                for (int ty = 0; ty < g.TH; ++ty)
+                    for (int ch = 0; ch < chunks; ++ch)
+                        for (int xg = 0; xg < L.xr_groups; ++xg)
+                            for (int t = 0; t < L.xr_ntaps[xg]; ++t) {
+                                const int kb = (ty * g.TW + L.xr_tx[xg][t]) * chunks + ch;
+                                mbar_wait(empty(s), ph ^ 1u);
+                                mbar_arrive_expect_tx(full_b(s), b_bytes);
+                                bulk_copy_g2s(xr_b_base + (uint32_t)s * xr_b_bytes, src + (size_t)kb * b_bytes, b_bytes, full_b(s));
+                                if (++s == xr_nb) { s = 0; ph ^= 1u; }
+                            }
+            }
+        }
     } else if (warp == 4) {
         // ------------------------------------------------------------------ B producer
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -343,61 +434,138 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
                 }
             }
         }
-    } else if (warp == 5) {
-        // ------------------------------------------------------------------ MMA issuer
-        int s = 0;
-        uint32_t ph = 0;
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-            const int ks = tile / mn_tiles;
-            const int nt = (tile - ks * mn_tiles) % num_nt;
-            const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
-            int bn = g.N - nt * TC_BN;
-            bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
-            // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
-            // N >> 3 in [17,23), M >> 4 in [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            const int ab = lt & 1;
-            const uint32_t acc = tmem_base + (uint32_t)(ab * TC_BN);
-            mbar_wait(tmem_empty(ab), (((uint32_t)lt >> 1) & 1u) ^ 1u);     // the epilogue drained this accumulator
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(full_a(s), ph);
-                mbar_wait(full_b(s), ph);
+    } else if (warp == 5 && L.xr) {
+        // ------------------------------------------------------------------ MMA issuer, tap reuse (one elected thread runs the loop)
+        if (elect_one()) {
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0;
+            int lt = 0;
+            // A descriptor high word: 10 rows of 128 bytes between the 8-row groups
+            constexpr uint32_t A_DESC_HI = (1280u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t da_ring = desc_lo(smem_base), db_ring = desc_lo(xr_b_base);
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const int nt = tile % num_nt;
+                int bn = g.N - nt * TC_BN;
+                bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                const uint32_t b_lo_step = ((uint32_t)bn * 128u) >> 4;
+                const int ab = lt & 1;
+                const uint32_t acc = tmem_base + (uint32_t)(ab * TC_BN);
+                mbar_wait(tmem_empty(ab), (((uint32_t)lt >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    // cp.async (generic proxy) wrote the A tiles; order them before the tensor core's
-                    // async-proxy reads
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    const uint32_t a_hi = smem_base + s * stage_bytes;
-                    const uint32_t a_lo = a_hi + A_PLANE;
-                    const uint32_t b_hi = a_hi + 2 * A_PLANE;
-                    const uint32_t b_lo = b_hi + (uint32_t)bn * 128u;
-                    // 16-wide K steps that hold data (the K tail of the last block is skipped, not multiplied by zero)
-                    int ksteps = (g.K - kb * TC_BK + 15) >> 4;
-                    if (ksteps > TC_BK / 16) ksteps = TC_BK / 16;
-                    const uint32_t da_hi = desc_lo(a_hi), da_lo = desc_lo(a_lo), db_hi = desc_lo(b_hi), db_lo = desc_lo(b_lo);
+                uint32_t accumulate = 0;
+                for (int ty = 0; ty < g.TH; ++ty) {
+                    for (int ch = 0; ch < chunks; ++ch) {
+                        for (int xg = 0; xg < L.xr_groups; ++xg) {
+                            mbar_wait(full_a(sa), pha);
+                            const int ntaps = L.xr_ntaps[xg];
+                            const bool last_group = ty == g.TH - 1 && ch == chunks - 1 && xg == L.xr_groups - 1;
+                            const uint32_t da_stage = da_ring + (uint32_t)sa * ((2u * XR_A_PLANE) >> 4);
+                            for (int t = 0; t < ntaps; ++t) {
+                                mbar_wait(full_b(sb), phb);
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                const uint32_t da_hi = da_stage + (uint32_t)L.xr_off[xg][t] * (128u >> 4);
+                                const uint32_t da_lo = da_hi + (XR_A_PLANE >> 4);
+                                const uint32_t db_hi = db_ring + (uint32_t)sb * (xr_b_bytes >> 4);
+                                const uint32_t db_lo = db_hi + b_lo_step;
+                                if (merged) {
 #pragma unroll
-                    for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
-                        if (k4 < ksteps) {                      // +2 per K step: 32 bytes >> 4 inside the 128-byte swizzle row
-                            if (merged) {
-                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc2, (kb > kb0 || k4 > 0) ? 1u : 0u);   // [hi*hi | hi*lo]
-                                umma_bf16(acc, da_lo + 2 * k4, db_hi + 2 * k4, idesc, 1u);                          // lo*hi
-                            } else {
-                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc, (kb > kb0 || k4 > 0) ? 1u : 0u);
+                                    for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                                        umma_bf16_x(acc, da_hi + 2 * k4, A_DESC_HI, db_hi + 2 * k4, idesc2, accumulate);   // [hi*hi | hi*lo]
+                                        umma_bf16_x(acc, da_lo + 2 * k4, A_DESC_HI, db_hi + 2 * k4, idesc, 1u);            // lo*hi
+                                        accumulate = 1u;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                                        umma_bf16_x(acc, da_hi + 2 * k4, A_DESC_HI, db_hi + 2 * k4, idesc, accumulate);
+                                        umma_bf16_x(acc, da_hi + 2 * k4, A_DESC_HI, db_lo + 2 * k4, idesc, 1u);
+                                        umma_bf16_x(acc, da_lo + 2 * k4, A_DESC_HI, db_hi + 2 * k4, idesc, 1u);
+                                        accumulate = 1u;
+                                    }
+                                }
+                                umma_commit(empty(sb));
+                                if (t == ntaps - 1) {
+                                    umma_commit(empty_a(sa));
+                                    if (last_group) umma_commit(tmem_full(ab));
+                                }
+                                if (++sb == xr_nb) { sb = 0; phb ^= 1u; }
+                            }
+                            if (++sa == xr_na) { sa = 0; pha ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ MMA issuer (one elected thread runs the loop)
+        if (elect_one()) {
+            int s = 0;
+            uint32_t ph = 0;
+            int lt = 0;
+            const uint32_t d_ring = desc_lo(smem_base), d_stage = stage_bytes >> 4;
+            // 16-wide K steps of the last K block that hold data (the K tail is skipped, not multiplied by zero)
+            const int last_ksteps = (g.K - (num_kb - 1) * TC_BK + 15) >> 4;
+            const bool needs_proxy_fence = !L.tma && !(L.debug_flags & 8);   // cp.async (generic proxy) wrote the A tiles
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+                const int ks = tile / mn_tiles;
+                const int nt = (tile - ks * mn_tiles) % num_nt;
+                const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+                int bn = g.N - nt * TC_BN;
+                bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
+                // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
+                // N >> 3 in [17,23), M >> 4 in [24,29)
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                const uint32_t b_lo_step = ((uint32_t)bn * 128u) >> 4;
+                const int ab = lt & 1;
+                const uint32_t acc = tmem_base + (uint32_t)(ab * TC_BN);
+                mbar_wait(tmem_empty(ab), (((uint32_t)lt >> 1) & 1u) ^ 1u);     // the epilogue drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t accumulate = 0;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    if (!(L.debug_flags & 64)) {
+                        mbar_wait(full_a(s), ph);
+                        mbar_wait(full_b(s), ph);
+                    }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // order the generic-proxy writes of the A tiles before the tensor core's async-proxy reads
+                    if (needs_proxy_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t da_hi = d_ring + (uint32_t)s * d_stage;
+                    const uint32_t da_lo = da_hi + (A_PLANE >> 4);
+                    const uint32_t db_hi = da_hi + ((2 * A_PLANE) >> 4);
+                    const uint32_t db_lo = db_hi + b_lo_step;
+                    int ksteps = kb == num_kb - 1 ? last_ksteps : TC_BK / 16;
+                    if (L.debug_flags & 16) ksteps = 1;
+                    if (merged) {
+#pragma unroll
+                        for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                            if (k4 < ksteps) {                  // +2 per K step: 32 bytes >> 4 inside the 128-byte swizzle row
+                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc2, accumulate);   // [hi*hi | hi*lo]
+                                umma_bf16(acc, da_lo + 2 * k4, db_hi + 2 * k4, idesc, 1u);            // lo*hi
+                                accumulate = 1u;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k4 = 0; k4 < TC_BK / 16; ++k4) {
+                            if (k4 < ksteps) {
+                                umma_bf16(acc, da_hi + 2 * k4, db_hi + 2 * k4, idesc, accumulate);
                                 umma_bf16(acc, da_hi + 2 * k4, db_lo + 2 * k4, idesc, 1u);
                                 umma_bf16(acc, da_lo + 2 * k4, db_hi + 2 * k4, idesc, 1u);
+                                accumulate = 1u;
                             }
                         }
                     }
-                    umma_commit(empty(s));
+                    if (L.debug_flags & 32) mbar_arrive(empty(s));
+                    else umma_commit(empty(s));
                     if (kb == kb1 - 1) umma_commit(tmem_full(ab));
+                    if (++s == num_stages) { s = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++s == num_stages) { s = 0; ph ^= 1u; }
             }
         }
+        __syncwarp();
     } else if (warp >= 8) {
         // ------------------------------------------------------------------ epilogue warps (set 0: 8..11, set 1: 12..15)
         const int set = (warp - 8) >> 2;                     // = accumulator buffer this set drains
@@ -508,11 +676,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
                             f0 = leaky_relu(f0);
                             f1 = leaky_relu(f1);
                         }
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(f0, h0, l0);
-                        split_bf16(f1, h1, l1);
-                        hi[jj] = pack_bf16(h0, h1);
-                        lo[jj] = pack_bf16(l0, l1);
+                        split_bf16x2(f0, f1, hi[jj], lo[jj]);
                     }
                     const uint32_t off = (uint32_t)lane * 64u + (uint32_t)((ch ^ ((lane >> 1) & 3)) << 4);
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
@@ -573,11 +737,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(GemmLaunch L) {
             f0 = leaky_relu(f0);
             f1 = leaky_relu(f1);
         }
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(f0, h0, l0);
-        split_bf16(f1, h1, l1);
-        hi[jj] = pack_bf16(h0, h1);
-        lo[jj] = pack_bf16(l0, l1);
+        split_bf16x2(f0, f1, hi[jj], lo[jj]);
     }
     const RowStep rs = make_row_step(g, 1u);
     const int64_t o = out_offset(g, row_init(rs, (unsigned)m)) + n;
@@ -617,10 +777,10 @@ static int log2_pow2_divisor(int v, int cap) {   // log2 of the largest power of
 }
 
 // NHWC activation plane [n, IH, IW, Cin] as a rank-4 tensor map with a (64 channels, bw pixels, bh pixels, nb samples) box
-static bool make_act_map(CUtensorMap* map, const void* base, const GemmGeom& g, int n, int bw, int bh, int nb) {
+static bool make_act_map(CUtensorMap* map, const void* base, const GemmGeom& g, int n, int bw, int bh, int nb, int extra_x = 0) {
     const cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.IW, (cuuint64_t)g.IH, (cuuint64_t)n};
     const cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.IW * g.Cin * 2, (cuuint64_t)g.in_sample_stride * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)(bw * g.sx_o), (cuuint32_t)(bh * g.sy_o), (cuuint32_t)nb};
+    const cuuint32_t box[4] = {64, (cuuint32_t)((bw + extra_x) * g.sx_o), (cuuint32_t)(bh * g.sy_o), (cuuint32_t)nb};
     const cuuint32_t estr[4] = {1, (cuuint32_t)g.sx_o, (cuuint32_t)g.sy_o, 1};
     return g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -645,6 +805,7 @@ int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
     memset(&map_hi, 0, sizeof(map_hi));
     memset(&map_lo, 0, sizeof(map_lo));
     L.tma = 0;
+    L.xr = 0;
     // real convolutions with 64-channel K blocks, forward stride (tconv phases walk taps backwards with sx_o = 1: fine)
     if (g_tma_enabled && g.TH * g.TW > 1 && g.Cin % 64 == 0 && g.sx_o >= 1 && g.sy_o >= 1 && g.sx_o <= 2 && g.sy_o <= 2 &&
         g.P == (g.P / g.OW) * g.OW && L.M % g.P == 0) {
@@ -657,17 +818,56 @@ int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
             }
         }
         const int OH = g.P / g.OW;
-        const int bwl = log2_pow2_divisor(g.OW, TC_BM);
+        // tap reuse along x: boxes of 8 output columns, every kernel-row group within 2 extra box elements
+        static const int xr_enabled = getenv("PNN_XREUSE") ? atoi(getenv("PNN_XREUSE")) != 0 : 1;
+        L.xr = 0;
+        if (xr_enabled && g.OW % 8 == 0 && g.N <= 128 && L.split_k <= 1 && g.TW <= 5 && !L.debug_flags) {
+            bool ok = true;
+            int ng = 0;
+            for (int rho = 0; rho < g.sx_o && ok; ++rho) {
+                int min_t = 1 << 30, cnt = 0;
+                for (int tx = 0; tx < g.TW; ++tx) {
+                    const int v = tx * g.sx_t;
+                    if (((v % g.sx_o) + g.sx_o) % g.sx_o == rho) {
+                        min_t = v < min_t ? v : min_t;
+                        ++cnt;
+                    }
+                }
+                if (cnt == 0) continue;
+                if (cnt > 3) { ok = false; break; }
+                int t = 0;
+                for (int tx = 0; tx < g.TW; ++tx) {
+                    const int v = tx * g.sx_t;
+                    if (((v % g.sx_o) + g.sx_o) % g.sx_o != rho) continue;
+                    const int off = (v - min_t) / g.sx_o;
+                    if (off > 2) ok = false;
+                    L.xr_tx[ng][t] = tx;
+                    L.xr_off[ng][t] = off;
+                    ++t;
+                }
+                L.xr_start[ng] = min_t + g.cx;
+                L.xr_ntaps[ng] = cnt;
+                ++ng;
+            }
+            if (ok && ng >= 1) {
+                L.xr = 1;
+                L.xr_groups = ng;
+            }
+        }
+        const int bwl = L.xr ? 3 : log2_pow2_divisor(g.OW, TC_BM);
         const int bhl = log2_pow2_divisor(OH, TC_BM >> bwl);
         const int bw = 1 << bwl, bh = 1 << bhl, nb = TC_BM / (bw * bh);
         const int n = L.M / g.P;
-        if (g_encode_tiled && bw * g.sx_o <= 256 && bh * g.sy_o <= 256 && make_act_map(&map_hi, L.in.p0, g, n, bw, bh, nb) &&
-            make_act_map(&map_lo, L.in.p1, g, n, bw, bh, nb)) {
+        const int extra_x = L.xr ? 2 : 0;
+        if (g_encode_tiled && (bw + extra_x) * g.sx_o <= 256 && bh * g.sy_o <= 256 &&
+            make_act_map(&map_hi, L.in.p0, g, n, bw, bh, nb, extra_x) && make_act_map(&map_lo, L.in.p1, g, n, bw, bh, nb, extra_x)) {
             L.tma = 1;
             L.bw_log2 = bwl;
             L.bh_log2 = bhl;
             L.x_tiles = g.OW / bw;
             L.y_tiles = OH / bh;
+        } else {
+            L.xr = 0;
         }
     }
     const int num_nt = (g.N + TC_BN - 1) / TC_BN;

@@ -16,6 +16,15 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// Two values at once -> packed (hi0 | hi1 << 16), (lo0 | lo1 << 16); same bits as split_bf16 on each value.  One
+// cvt.rn.bf16x2.f32 (F2FP, ALU pipe) per pair and plane instead of two scalar F2F.BF16.F32, which issue at a fraction of
+// the rate and made the epilogues of the small-K layers conversion-bound.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
 template <bool SPLIT>
 __device__ __forceinline__ float act_load(const Act& a, int64_t idx) {
     if (SPLIT) {

@@ -1,4 +1,4 @@
-// HBM / latency-bound kernels of the PNN path: fused context gathers, im2col of the first convolution, channel-wise
+// HBM / latency-bound kernels of the PNN path: fused context gathers, the direct first convolution, channel-wise
 // merger, col2im of the last transposed convolution with the fused epilogue, PSNR / win flags, and the batch-1
 // fully-connected kernels of the in-loop path.
 #include "kernels_common.cuh"
@@ -345,56 +345,117 @@ int launch_convert_input(const float* src, Act dst, int64_t n, int split, cudaSt
 }
 
 // ---------------------------------------------------------------------------------------------
-// im2col for the first convolution (1 input channel): thread = (output pixel, group of 8 taps).  The
-// convolution itself then runs on the tensor cores as a GEMM with K = KP (reference pnn/tfutils.py:134-139).
+// First convolution of a branch, direct form (reference pnn/tfutils.py:134-139 with one input channel, then
+// pnn/components.py:44-52 LeakyReLU).  Thread = PR output pixels of one column (rows PR*g .. PR*g + PR-1) x 16 output
+// channels; lanes = consecutive columns.  The weights live in the kernel-parameter constant bank and every loop is
+// unrolled, so the FFMAs take their weights through the uniform datapath (LDCU.128 + FFMA R, R, UR, R): no shared
+// memory, no weight loads on the LSU, ((PR-1)*S + K) x K scalar input loads (L1) per PR*16*K*K FFMA.  One kernel per
+// channel group keeps the straight-line code of a launch small (a switch over the group inside one kernel stalled on
+// instruction fetch).  PR = 2 (96 registers, 20 warps / SM) measured faster than PR = 4 (166 registers, 12 warps).
+// Fixed summation order (ky, kx ascending).  Output: bias, LeakyReLU, hi/lo split, one 32-byte store per pixel and plane.
 // ---------------------------------------------------------------------------------------------
-template <bool SPLIT>
-__global__ void __launch_bounds__(256) im2col_kernel(Im2colLaunch L) {
-    const int P = L.OH * L.OW;
-    const int groups = L.KP >> 3;                       // 8 taps per thread
-    const int ppb = 256 / groups;                       // pixels per block
-    const int tiles = (P + ppb - 1) / ppb;
-    const int b = blockIdx.x / tiles, tile = blockIdx.x - b * tiles;
-    const int pix = tile * ppb + threadIdx.x / groups;
-    const int grp = threadIdx.x % groups;
-    if (pix >= P) return;
-    const int oy = pix / L.OW, ox = pix - oy * L.OW;
-    const float* in = L.in + (int64_t)b * L.IH * L.IW;
-    float v[8];
+constexpr int CF_THREADS = 128;
+
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+template <int K, int S, bool SPLIT, int CG, int PR>
+__global__ void __launch_bounds__(CF_THREADS, PR == 4 ? 3 : 5) conv_first_kernel(const __grid_constant__ ConvFirstLaunch L,
+                                                                                 const __grid_constant__ ConvFirstWeights Wt) {
+    const unsigned OW = (unsigned)L.OW, groups = (unsigned)L.OH / PR;
+    const int64_t total = (int64_t)L.n * groups * OW;
+    constexpr int NR = (PR - 1) * S + K;                           // input rows feeding PR output rows
+    for (int64_t t = (int64_t)blockIdx.x * CF_THREADS + threadIdx.x; t < total; t += (int64_t)gridDim.x * CF_THREADS) {
+        const unsigned r0 = (unsigned)(t / OW), ox = (unsigned)(t - (int64_t)r0 * OW);
+        const unsigned b = r0 / groups, g = r0 - b * groups;
+        const float* inb = L.in + (int64_t)b * L.IH * L.IW;
+        float acc[PR][16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int t = grp * 8 + j;
-        const int ky = t / L.k, kx = t - ky * L.k;
-        const int iy = oy * L.stride + ky - L.pad, ix = ox * L.stride + kx - L.pad;
-        v[j] = (t < L.k * L.k && iy >= 0 && iy < L.IH && ix >= 0 && ix < L.IW) ? __ldg(in + iy * L.IW + ix) : 0.f;
-    }
-    const int64_t o = ((int64_t)b * P + pix) * L.KP + grp * 8;
-    if (SPLIT) {
-        uint32_t hi[4], lo[4];
+        for (int p = 0; p < PR; ++p)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[2 * j], h0, l0);
-            split_bf16(v[2 * j + 1], h1, l1);
-            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            for (int c = 0; c < 16; ++c) acc[p][c] = 0.f;
+        const int ix0 = (int)ox * S - L.pad, iy0 = (int)g * PR * S - L.pad;
+        // all NR x K input values of the item first (independent loads), then tap-major FFMAs: a weight is fetched once
+        // and used for the PR pixels right away
+        float v[NR][K];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int iy = iy0 + r;
+            const bool row_ok = (unsigned)iy < (unsigned)L.IH;
+            const float* row = inb + (row_ok ? iy : 0) * L.IW;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int ix = ix0 + kx;
+                v[r][kx] = (row_ok && (unsigned)ix < (unsigned)L.IW) ? __ldg(row + ix) : 0.f;
+            }
         }
-        *(uint4*)((__nv_bfloat16*)L.out.p0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *(uint4*)((__nv_bfloat16*)L.out.p1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    } else {
-        float4* po = (float4*)((float*)L.out.p0 + o);
-        po[0] = make_float4(v[0], v[1], v[2], v[3]);
-        po[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const float w = Wt.w[(ky * K + kx) * 64 + CG * 16 + c];
+#pragma unroll
+                    for (int p = 0; p < PR; ++p) acc[p][c] = fmaf(v[p * S + ky][kx], w, acc[p][c]);
+                }
+#pragma unroll
+        for (int p = 0; p < PR; ++p) {
+            const int64_t pix = ((int64_t)b * L.OH + g * PR + p) * OW + ox;
+            const int64_t o = pix * L.C + CG * 16;
+            float y[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float z = acc[p][c] + Wt.b[CG * 16 + c];
+                y[c] = fmaxf(z, 0.1f * z);
+            }
+            if (SPLIT) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    split_bf16x2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+                }
+                st_global_v8((__nv_bfloat16*)L.out.p0 + o, hi);
+                st_global_v8((__nv_bfloat16*)L.out.p1 + o, lo);
+            } else {
+                uint32_t u[8];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(y[half * 8 + j]);
+                    st_global_v8((float*)L.out.p0 + o + half * 8, u);
+                }
+            }
+        }
     }
 }
 
-int launch_im2col(const Im2colLaunch& L, cudaStream_t stream) {
+template <int K, int S, bool SPLIT, int PR>
+void conv_first_launch_groups(const ConvFirstLaunch& L, const ConvFirstWeights& W, unsigned grid, cudaStream_t stream) {
+    conv_first_kernel<K, S, SPLIT, 0, PR><<<grid, CF_THREADS, 0, stream>>>(L, W);
+    conv_first_kernel<K, S, SPLIT, 1, PR><<<grid, CF_THREADS, 0, stream>>>(L, W);
+    if (L.C == 64) {
+        conv_first_kernel<K, S, SPLIT, 2, PR><<<grid, CF_THREADS, 0, stream>>>(L, W);
+        conv_first_kernel<K, S, SPLIT, 3, PR><<<grid, CF_THREADS, 0, stream>>>(L, W);
+    }
+}
+
+int launch_conv_first(const ConvFirstLaunch& L, const ConvFirstWeights& W, cudaStream_t stream) {
     if (L.n == 0) return 0;
-    const int P = L.OH * L.OW, ppb = 256 / (L.KP / 8);
-    const int64_t grid = (int64_t)L.n * ((P + ppb - 1) / ppb);
-    if (L.split) im2col_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(L);
-    else im2col_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(L);
-    return 1;
+    constexpr int PR = 2;
+    const int64_t total = (int64_t)L.n * (L.OH / PR) * L.OW;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + CF_THREADS - 1) / CF_THREADS, 148 * 20);
+    if (L.k == 5 && L.stride == 2) {
+        if (L.split) conv_first_launch_groups<5, 2, true, PR>(L, W, grid, stream);
+        else conv_first_launch_groups<5, 2, false, PR>(L, W, grid, stream);
+    } else {
+        if (L.split) conv_first_launch_groups<3, 1, true, PR>(L, W, grid, stream);
+        else conv_first_launch_groups<3, 1, false, PR>(L, W, grid, stream);
+    }
+    return L.C / 16;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -547,11 +608,7 @@ __global__ void __launch_bounds__(256, 1) merger_kernel(MergerLaunch L, int grou
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(y[2 * j], h0, l0);
-                    split_bf16(y[2 * j + 1], h1, l1);
-                    hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    split_bf16x2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
                 }
                 *(uint4*)((__nv_bfloat16*)L.out.p0 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *(uint4*)((__nv_bfloat16*)L.out.p1 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

@@ -84,7 +84,7 @@ T* upload(const std::vector<T>& v, std::vector<std::unique_ptr<DevBuf>>& keep) {
     return (T*)keep.back()->p;
 }
 
-enum StepKind { STEP_GEMM, STEP_MERGER, STEP_IM2COL, STEP_COL2IM };
+enum StepKind { STEP_GEMM, STEP_MERGER, STEP_COL2IM, STEP_CONV_FIRST };
 
 struct Step {
     StepKind kind;
@@ -100,6 +100,7 @@ struct Step {
     // conv0
     int IH = 0, IW = 0, OH = 0, OW = 0, C = 0, k = 0, stride = 0, pad = 0, KP = 0;
     float bias_scalar = 0.f;
+    std::shared_ptr<ConvFirstWeights> conv_first;   // host copy: travels as a kernel parameter
 };
 
 struct Net {
@@ -308,23 +309,19 @@ void build_conv(Net& net, const FlatFile& ff) {
             Step st;
             st.in0 = cur;
             if (i == 0) {
-                // first convolution (one input channel): im2col (k*k taps padded to KP columns) + GEMM
                 if (pad_x != pad_y) throw std::runtime_error("unexpected asymmetric padding");
-                const int KP = (k * k + 15) / 16 * 16;
-                Step im;
-                im.kind = STEP_IM2COL;
-                im.in0 = cur;
-                im.out = add_buf(net, (int64_t)oh * ow * KP);
-                im.IH = h; im.IW = w; im.OH = oh; im.OW = ow; im.k = k; im.stride = s; im.pad = pad_y; im.KP = KP;
-                net.steps.push_back(im);
-                st.kind = STEP_GEMM;
-                st.in0 = im.out;
+                // first convolution (one input channel): direct FFMA kernel, weights [k*k][C] as stored
+                if ((c != 32 && c != 64) || oh % 2 || !((k == 5 && s == 2) || (k == 3 && s == 1))) {
+                    throw std::runtime_error("unexpected first convolution");
+                }
+                st.kind = STEP_CONV_FIRST;
                 st.out = add_buf(net, (int64_t)oh * ow * c);
-                st.g = pixel_gemm_geom(oh, ow, KP, c, 1);
-                std::vector<float> wkn((size_t)KP * c, 0.f);
+                st.IH = h; st.IW = w; st.OH = oh; st.OW = ow; st.k = k; st.stride = s; st.pad = pad_y; st.C = c;
+                st.conv_first.reset(new ConvFirstWeights());
+                memset(st.conv_first.get(), 0, sizeof(ConvFirstWeights));
                 for (int t = 0; t < k * k; ++t)
-                    for (int co = 0; co < c; ++co) wkn[(size_t)t * c + co] = wt[(size_t)t * c + co];   // [k,k,1,Cout]
-                add_gemm_weights(net, st, wkn, bs);
+                    for (int co = 0; co < c; ++co) st.conv_first->w[t * 64 + co] = wt[(size_t)t * c + co];   // [k,k,1,C]
+                for (int co = 0; co < c; ++co) st.conv_first->b[co] = bs[co];
             } else {
                 st.out = add_buf(net, (int64_t)oh * ow * c);
                 st.kind = STEP_GEMM;
@@ -624,14 +621,14 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 h->launches += launch_merger(L, stream);
                 break;
             }
-            case STEP_IM2COL: {
-                Im2colLaunch L{};
+            case STEP_CONV_FIRST: {
+                ConvFirstLaunch L{};
                 L.in = (const float*)net.ws0[st.in0]->p;
                 L.out = act_of(net, st.out);
-                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.OH = st.OH; L.OW = st.OW; L.k = st.k; L.stride = st.stride;
-                L.pad = st.pad; L.KP = st.KP; L.split = split;
-                ProfScope ps(h, stream, "im2col", n * st.OH * st.OW, st.KP, 1, false);
-                h->launches += launch_im2col(L, stream);
+                L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.OH = st.OH; L.OW = st.OW; L.C = st.C; L.k = st.k;
+                L.stride = st.stride; L.pad = st.pad; L.split = split;
+                ProfScope ps(h, stream, "conv_first", n * st.OH * st.OW, st.C, st.k * st.k, false);
+                h->launches += launch_conv_first(L, *st.conv_first, stream);
                 break;
             }
             case STEP_COL2IM: {

@@ -62,7 +62,8 @@ struct GemmLaunch {
     const float* w_fp32;        // [K][N] fp32 (fp32 precision)
     const uint8_t* w_tiles;     // pre-swizzled bf16 hi/lo tiles (bf16x3 precision)
     const float* bias;          // [N]
-    int debug_flags;            // tuning aid: bit 0 skip A loads, bit 1 skip B loads, bit 2 skip epilogue stores
+    int debug_flags;            // tuning aid (pnn_debug_time_gemm): bit 0 skip A loads, 1 skip B loads, 2 skip epilogue stores,
+                                // 3 no proxy fence, 4 one K step per block, 5 plain arrive instead of tcgen05.commit, 6 issuer skips waits
     // split-K (in-loop batch-1 path only, where 1-2 tiles would otherwise walk K serially): slice ks of the K blocks
     // writes its raw fp32 accumulators to partial[ks][M][N]; splitk_reduce adds the slices in ascending order, then
     // bias / LeakyReLU / hi-lo split.  1 = off.
@@ -73,6 +74,17 @@ struct GemmLaunch {
     // plane and K block (hardware 128B swizzle, zero fill for SAME padding, element strides for stride 2).
     int tma;                    // 1: tile = (sample tile, y tile, x tile, n tile), rows in box order
     int bw_log2, bh_log2, x_tiles, y_tiles;
+    // Tap reuse along x (TMA path, bw = 8, N <= 128): the taps of one kernel row whose input columns differ by whole
+    // box elements share ONE box that is 2 pixels wider (10 x bh x nb rows of 128 B); tap t is reached by starting
+    // the tcgen05 shared-memory descriptor xr_off rows further (the 128B swizzle is a function of the absolute
+    // shared-memory address, tools/probes/umma_desc_probe.cu), with 10 rows between the 8-row groups.  K order:
+    // (ty, 64-channel chunk, group, tap).  Stride-2 convolutions have two groups (even / odd columns).
+    int xr;                     // 1: on
+    int xr_groups;
+    int xr_start[2];            // first input column of the group's box relative to ox0 * sx_o
+    int xr_ntaps[2];
+    int xr_tx[2][3];
+    int xr_off[2][3];
 };
 int launch_splitk_reduce(const GemmLaunch& L, cudaStream_t stream);
 
@@ -109,14 +121,20 @@ void gemm_tc_set_tma(int enabled);
 // one-time opt-in for the tcgen05 kernel's dynamic shared memory
 cudaError_t gemm_tc_init();
 
-// im2col of a one-channel context portion for the first convolution: row (b, oy, ox) gets the k*k taps
-// (zero outside the map, SAME padding) followed by zeros up to KP columns.
-struct Im2colLaunch {
-    const float* in;     // [n, IH, IW] fp32
-    Act out;             // [n*OH*OW, KP]
-    int n, IH, IW, OH, OW, k, stride, pad, KP, split;
+// First convolution of a branch (one input channel) as a direct fp32 FFMA kernel fused with bias, LeakyReLU and the
+// hi/lo split: replaces im2col + GEMM (K = k*k is too small for the tensor pipe to matter; the layer is bound by
+// writing its C-channel output).
+struct ConvFirstWeights {
+    float w[25 * 64];    // [tap][64]: TF layout [k, k, 1, C], rows padded to 64 channels
+    float b[64];
 };
-int launch_im2col(const Im2colLaunch& L, cudaStream_t stream);
+struct ConvFirstLaunch {
+    const float* in;     // [n, IH, IW] fp32
+    Act out;             // [n*OH*OW, C]
+    int n, IH, IW, OH, OW, C, k, stride, pad, split;
+};
+// One launch per group of 16 output channels (C / 16 launches); returns the number of launches.
+int launch_conv_first(const ConvFirstLaunch& L, const ConvFirstWeights& W, cudaStream_t stream);
 
 // col2im of the last transposed convolution + the output epilogue: D[(b, iy, ix), ky*k+kx] holds the
 // per-tap dot products (GEMM output); out[y, x] = bias + sum over the taps with iy*s + ky - pad == y.

@@ -11,6 +11,6 @@ shapes = [(M, 1200, 1200), (M, 1280, 1200), (M, 1200, 1216), (M, 1200, 1280), (M
 if len(sys.argv) > 1:
     shapes = [tuple(int(v) for v in a.split('x')) for a in sys.argv[1:]]
 for (m, n, k) in shapes:
-    for flags in (0, 1, 2, 4, 3, 7):
+    for flags in [int(v) for v in os.environ.get("FLAGS", "0,1,2,4,3,7").split(",")]:
         ms = eng.time_gemm(m, n, k, 5, flags)
         print('%8d %6d %6d %6d  %8.3f %8.1f' % (m, n, k, flags, ms, 2. * m * n * k / ms / 1e9), flush=True)

@@ -7,7 +7,7 @@ import helpers
 from context_adaptive_neural_network_based_prediction_b200 import Engine
 eng = Engine(); tmp = tempfile.mkdtemp()
 img = numpy.stack([helpers.synthetic_image(96, 128, s) for s in range(2)])
-for width, is_fc in ((4, True), (8, False), (16, False)):
+for width, is_fc in ((4, True), (8, False), (16, False), (32, False)):
     path, _ = helpers.make_net_file(tmp, width, is_fc, seed=width)
     eng.load_net(path)
     r, c = helpers.grid_blocks(96, 128, width)
