@@ -622,20 +622,162 @@ __global__ void __launch_bounds__(256, 1) merger_kernel(MergerLaunch L, int grou
 }
 
 static int g_merger_init = 0;
+constexpr int MG5_THREADS = 128;
+constexpr int MG5_SMEM = 2 * 5 * 8 * 2 * 32 * 16;    // [octet][k16 chunk][channel][n tile][lane] x {b0_hi, b1_hi, b0_lo, b1_lo}
+__global__ void merger_mma_kernel(MergerLaunch L, int groups);
 
 void small_kernels_init() {
+    cudaFuncSetAttribute(merger_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG5_SMEM);
     cudaFuncSetAttribute(merger_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
     cudaFuncSetAttribute(merger_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
     g_merger_init = 1;
+}
+
+// v5 (bf16x3 precision): the same per-channel [samples x 80] x [80 x 16] products on the tensor cores, through the
+// warp-level mma.sync path because its operands are REGISTER fragments: the activations are channel-last ([sample, q, C]),
+// so a K-major shared-memory operand for one channel (what tcgen05 needs) would cost a transpose through shared memory,
+// whereas here a lane's 16-byte load (8 channels of one (sample, q)) feeds 8 channel problems after one PRMT per
+// fragment register.  The op is bound by HBM (98 KB per sample at C = 256 against 0.65 MFLOP), the FFMA version (v4,
+// kept for the fp32 yard-stick) was bound by the LSU: 32 broadcast LDS.128 per 128 FFMA, ncu l1tex 88 %, FMA pipe 23 %.
+// Warp = 16 samples x 8 channels: per 16 positions 16 LDG.128 + 16 LDS.128 (weight fragments, prepared once per CTA in
+// the exact per-lane order) + 64 PRMT + 48 mma.m16n8k16 (hi*hi, hi*lo, lo*hi; fp32 accumulate, q ascending).
+// CTA = 4 warps = 2 channel octets x 2 sample halves, so that both halves of every 32-byte sector are consumed by the
+// same SM; persistent over sample tiles.  Fragment layout (PTX ISA, m16n8k16 .bf16): g = lane >> 2, t = lane & 3;
+// A: a0 (row g, k 2t..2t+1), a1 (row g+8, same k), a2 (row g, k 2t+8..2t+9), a3 (row g+8, k 2t+8..); B: b0 (k 2t..2t+1,
+// n g), b1 (k 2t+8.., n g); C: c0, c1 (row g, n 2t, 2t+1), c2, c3 (row g+8, same n).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t u4_word(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+__global__ void __launch_bounds__(MG5_THREADS, 2) merger_mma_kernel(MergerLaunch L, int groups) {
+    extern __shared__ __align__(16) uint8_t mg5_smem[];
+    uint4* wfrag = reinterpret_cast<uint4*>(mg5_smem);
+    const int C = L.C;
+    const int pair = blockIdx.x / groups, grp = blockIdx.x - pair * groups;    // channel group of 16, sample-tile group
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    // weight fragments of the CTA's 16 channels: hi/lo split once
+    for (int idx = threadIdx.x; idx < 2 * 5 * 8 * 2 * 32; idx += MG5_THREADS) {
+        const int ln = idx & 31, nt = (idx >> 5) & 1, j = (idx >> 6) & 7, kc = (idx >> 9) % 5, oct = idx / (5 * 512);
+        const int gg = ln >> 2, tt = ln & 3;
+        const int c = pair * 16 + oct * 8 + j, n = nt * 8 + gg;
+        const int ks[4] = {kc * 16 + 2 * tt, kc * 16 + 2 * tt + 1, kc * 16 + 2 * tt + 8, kc * 16 + 2 * tt + 9};
+        float w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = __ldg(L.w + ((int64_t)ks[i] * 16 + n) * C + c);
+        uint4 f;
+        split_bf16x2(w[0], w[1], f.x, f.z);
+        split_bf16x2(w[2], w[3], f.y, f.w);
+        wfrag[idx] = f;
+    }
+    __syncthreads();
+    const int oct = warp & 1, half = warp >> 1;
+    const int c0 = pair * 16 + oct * 8;
+    const uint4* wf = wfrag + oct * (5 * 512) + lane;
+    const __nv_bfloat16* in0_hi = (const __nv_bfloat16*)L.in0.p0 + c0;
+    const __nv_bfloat16* in0_lo = (const __nv_bfloat16*)L.in0.p1 + c0;
+    const __nv_bfloat16* in1_hi = (const __nv_bfloat16*)L.in1.p0 + c0;
+    const __nv_bfloat16* in1_lo = (const __nv_bfloat16*)L.in1.p1 + c0;
+    const int tiles = (L.n + 31) >> 5;                        // 32 samples per CTA iteration
+    for (int tile = grp; tile < tiles; tile += groups) {
+        const int s_base = tile * 32 + half * 16;
+        if (s_base >= L.n) continue;                          // warp-uniform
+        // the two samples (fragment rows g and g + 8) of this lane, clamped for the loads
+        const int sa = min(s_base + g, L.n - 1), sb = min(s_base + g + 8, L.n - 1);
+        float acc[8][2][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[j][nt][i] = 0.f;
+#pragma unroll
+        for (int kc = 0; kc < 5; ++kc) {
+            // positions q = kc*16 + {2t, 2t+1, 2t+8, 2t+9}: q < 48 lies in the above map (48 positions), else in the left map
+            const bool above = kc < 3;
+            const __nv_bfloat16* ph = above ? in0_hi : in1_hi;
+            const __nv_bfloat16* pl = above ? in0_lo : in1_lo;
+            const int npos = above ? 48 : 32, q0 = (above ? kc * 16 : (kc - 3) * 16) + 2 * t;
+            const int64_t ra = ((int64_t)sa * npos + q0) * C, rb = ((int64_t)sb * npos + q0) * C;
+            // x[row][i]: row 0 = sample g, row 1 = sample g + 8; i = position 2t, 2t+1, 2t+8, 2t+9
+            uint4 xh[2][4], xl[2][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t dq = (int64_t)((i & 1) + (i >> 1) * 8) * C;
+                xh[0][i] = __ldg((const uint4*)(ph + ra + dq));
+                xh[1][i] = __ldg((const uint4*)(ph + rb + dq));
+                xl[0][i] = __ldg((const uint4*)(pl + ra + dq));
+                xl[1][i] = __ldg((const uint4*)(pl + rb + dq));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+                uint32_t ah[4], al[4];
+                ah[0] = __byte_perm(u4_word(xh[0][0], j >> 1), u4_word(xh[0][1], j >> 1), sel);
+                ah[1] = __byte_perm(u4_word(xh[1][0], j >> 1), u4_word(xh[1][1], j >> 1), sel);
+                ah[2] = __byte_perm(u4_word(xh[0][2], j >> 1), u4_word(xh[0][3], j >> 1), sel);
+                ah[3] = __byte_perm(u4_word(xh[1][2], j >> 1), u4_word(xh[1][3], j >> 1), sel);
+                al[0] = __byte_perm(u4_word(xl[0][0], j >> 1), u4_word(xl[0][1], j >> 1), sel);
+                al[1] = __byte_perm(u4_word(xl[1][0], j >> 1), u4_word(xl[1][1], j >> 1), sel);
+                al[2] = __byte_perm(u4_word(xl[0][2], j >> 1), u4_word(xl[0][3], j >> 1), sel);
+                al[3] = __byte_perm(u4_word(xl[1][2], j >> 1), u4_word(xl[1][3], j >> 1), sel);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const uint4 b = wf[((kc * 8 + j) * 2 + nt) * 32];      // {b0_hi, b1_hi, b0_lo, b1_lo}
+                    mma_bf16_16816(acc[j][nt], ah, b.x, b.y);               // hi * hi
+                    mma_bf16_16816(acc[j][nt], ah, b.z, b.w);               // hi * lo
+                    mma_bf16_16816(acc[j][nt], al, b.x, b.y);               // lo * hi
+                }
+            }
+        }
+        // epilogue: (sample, output) pairs of this lane: rows {g, g+8} x outputs {2t, 2t+1, 8+2t, 8+2t+1}; the 8 channels of
+        // a pair are the 8 accumulator sets -> one 16-byte store per plane
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+            const int smp = s_base + g + 8 * row;
+            if (smp >= L.n) continue;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int o = nt * 8 + 2 * t + e;
+                    const float4 b0 = __ldg((const float4*)(L.bias + (int64_t)o * C + c0));
+                    const float4 b1 = __ldg((const float4*)(L.bias + (int64_t)o * C + c0 + 4));
+                    const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float y[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = leaky_relu(acc[j][nt][2 * row + e] + bias[j]);
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) split_bf16x2(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+                    const int64_t off = ((int64_t)smp * 16 + o) * C + c0;
+                    *(uint4*)((__nv_bfloat16*)L.out.p0 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *(uint4*)((__nv_bfloat16*)L.out.p1 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+    }
 }
 
 int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
     if (L.n == 0) return 0;
     if (L.C % MG_CH) return -1;
     if (!g_merger_init) {
+        cudaFuncSetAttribute(merger_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MG5_SMEM);
         cudaFuncSetAttribute(merger_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
         cudaFuncSetAttribute(merger_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
         g_merger_init = 1;
+    }
+    static const int use_mma = getenv("PNN_MERGER_MMA") ? atoi(getenv("PNN_MERGER_MMA")) != 0 : 1;
+    if (L.split && use_mma) {
+        const int pairs = L.C / 16, tiles32 = (L.n + 31) / 32;
+        int groups5 = (2 * 148 + pairs - 1) / pairs;        // about two resident CTAs per SM
+        if (groups5 > tiles32) groups5 = tiles32;
+        merger_mma_kernel<<<pairs * groups5, MG5_THREADS, MG5_SMEM, stream>>>(L, groups5);
+        return 1;
     }
     const int ncg = L.C / MG_CH;
     const int tiles = (L.n + MG_TILE - 1) / MG_TILE;

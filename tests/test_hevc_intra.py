@@ -108,8 +108,10 @@ def test_offline_evaluation_keys_and_win_rate(engine, golden_dir):
     _, psnrs_hevc, _ = hevc_intra.best_modes_of_blocks(img[None], idx, rows, cols, width, 0, 0)
     freq = float(numpy.count_nonzero(psnrs_pnn - psnrs_hevc > 0.)) / len(rows)
     numpy.testing.assert_allclose(got['psnrs_hevc_best_mode'], psnrs_hevc, rtol=0, atol=1e-9)
-    same = (got['predictions_pnn_uint8'].reshape(len(rows), -1) == pred_u8.reshape(len(rows), -1)).all(axis=1)
-    assert same.mean() > 0.99
+    same_px = got['predictions_pnn_uint8'].reshape(len(rows), -1) == pred_u8.reshape(len(rows), -1)
+    assert same_px.mean() >= 0.999                       # BASELINE.json: >= 99.9 % identical rounded pixels
+    same = same_px.all(axis=1)                           # blocks without a single rounding flip
+    assert same.mean() > 0.95
     numpy.testing.assert_allclose(got['psnrs_pnn'][same], psnrs_pnn[same], rtol=0, atol=1e-9)
     assert abs(got['frequency_win_pnn'] - freq) <= (1. - same.mean()) + 1e-12
     assert set(('psnrs_pnn', 'indices_hevc_best_mode', 'psnrs_hevc_best_mode', 'mean_psnr_pnn', 'frequency_win_pnn')) <= set(got)
