@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
     // split-K: tile = (ks, mt, nt) with nt fastest; slice ks owns the K blocks [ks*kb_per, min(num_kb, (ks+1)*kb_per))
     const int split_k = L.split_k > 1 ? L.split_k : 1;
     const int kb_per = (num_kb + split_k - 1) / split_k;
+    const int unit = blockIdx.x, units = gridDim.x;
     const int mn_tiles = num_nt * num_mt;
     const int num_tiles = mn_tiles * split_k;
     // the widest tile fixes the stage size, hence the ring depth
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_lo) : "memory");
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += units) {
                 int r = tile / num_nt;
                 const int xt = r % L.x_tiles;
                 r /= L.x_tiles;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
             asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmap_lo) : "memory");
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += units) {
                 const int ks = tile / mn_tiles;
                 int r = (tile - ks * mn_tiles) / num_nt;
                 const int xt = r % L.x_tiles;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
         int cur_mt = -1;
         int64_t rbase[8];
         int rpos[8];
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit; tile < num_tiles; tile += units) {
             const int ks = tile / mn_tiles;
             const int mt = (tile - ks * mn_tiles) / num_nt;
             const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
         if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += units) {
                 const int nt = tile % num_nt;
                 int bn = g.N - nt * TC_BN;
                 bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
         if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += units) {
                 const int ks = tile / mn_tiles;
                 const int nt = (tile - ks * mn_tiles) % num_nt;
                 const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
             // A descriptor high word: 10 rows of 128 bytes between the 8-row groups
             constexpr uint32_t A_DESC_HI = (1280u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t da_ring = desc_lo(smem_base), db_ring = desc_lo(xr_b_base);
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            for (int tile = unit; tile < num_tiles; tile += units, ++lt) {
                 const int nt = tile % num_nt;
                 int bn = g.N - nt * TC_BN;
                 bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
             // 16-wide K steps of the last K block that hold data (the K tail is skipped, not multiplied by zero)
             const int last_ksteps = (g.K - (num_kb - 1) * TC_BK + 15) >> 4;
             const bool needs_proxy_fence = !L.tma && !(L.debug_flags & 8);   // cp.async (generic proxy) wrote the A tiles
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+            for (int tile = unit; tile < num_tiles; tile += units, ++lt) {
                 const int ks = tile / mn_tiles;
                 const int nt = (tile - ks * mn_tiles) % num_nt;
                 const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
         const RowStep rs8 = make_row_step(g, 8u);
         const RowStep rs1 = make_row_step(g, 1u);
         int j = 0;                                           // tiles this set has processed
-        for (int tile = blockIdx.x + set * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, ++j) {
+        for (int tile = unit + set * units; tile < num_tiles; tile += 2 * units, ++j) {
             const int ks = tile / mn_tiles;
             const int nt = (tile - ks * mn_tiles) % num_nt, mt = (tile - ks * mn_tiles) / num_nt;
             const int n0 = nt * TC_BN;
@@ -806,8 +807,15 @@ int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
     memset(&map_lo, 0, sizeof(map_lo));
     L.tma = 0;
     L.xr = 0;
+    // FC geometry (one tap, one position per sample, rows contiguous): a rank-4 map with a 1 x 1 x 128-sample box; the K tail
+    // of the last block is the map's out-of-bounds zero fill
+    static const int fc_tma_enabled = getenv("PNN_FC_TMA") ? atoi(getenv("PNN_FC_TMA")) != 0 : 1;
+    const bool fc_like = fc_tma_enabled && g.P == 1 && g.TH * g.TW == 1 && g.IH == 1 && g.IW == 1 && (g.Cin * 2) % 16 == 0 &&
+                         g.in_sample_stride == g.Cin && L.split_k <= 1;
+    GemmGeom gm = g;                       // geometry the tensor map is built from
+    if (fc_like) gm.sx_o = gm.sy_o = 1;
     // real convolutions with 64-channel K blocks, forward stride (tconv phases walk taps backwards with sx_o = 1: fine)
-    if (g_tma_enabled && g.TH * g.TW > 1 && g.Cin % 64 == 0 && g.sx_o >= 1 && g.sy_o >= 1 && g.sx_o <= 2 && g.sy_o <= 2 &&
+    if (g_tma_enabled && (fc_like || (g.TH * g.TW > 1 && g.Cin % 64 == 0 && g.sx_o >= 1 && g.sy_o >= 1 && g.sx_o <= 2 && g.sy_o <= 2)) &&
         g.P == (g.P / g.OW) * g.OW && L.M % g.P == 0) {
         if (!g_encode_tiled) {
             cudaDriverEntryPointQueryResult qres;
@@ -859,8 +867,8 @@ int launch_gemm_tc(const GemmLaunch& L_in, cudaStream_t stream) {
         const int bw = 1 << bwl, bh = 1 << bhl, nb = TC_BM / (bw * bh);
         const int n = L.M / g.P;
         const int extra_x = L.xr ? 2 : 0;
-        if (g_encode_tiled && (bw + extra_x) * g.sx_o <= 256 && bh * g.sy_o <= 256 &&
-            make_act_map(&map_hi, L.in.p0, g, n, bw, bh, nb, extra_x) && make_act_map(&map_lo, L.in.p1, g, n, bw, bh, nb, extra_x)) {
+        if (g_encode_tiled && (bw + extra_x) * gm.sx_o <= 256 && bh * gm.sy_o <= 256 &&
+            make_act_map(&map_hi, L.in.p0, gm, n, bw, bh, nb, extra_x) && make_act_map(&map_lo, L.in.p1, gm, n, bw, bh, nb, extra_x)) {
             L.tma = 1;
             L.bw_log2 = bwl;
             L.bh_log2 = bhl;
