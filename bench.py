@@ -255,6 +255,7 @@ def main():
     d_psnr = torch.empty(total, dtype=torch.float64, device=dev)
     d_win = torch.empty(total, dtype=torch.uint8, device=dev)
     d_base = torch.empty(total, dtype=torch.float64, device=dev)            # supplied baseline PSNRs: best HEVC intra mode
+    h_psnr_all = torch.empty(total, dtype=torch.float64).pin_memory()      # e2e arm: the PSNRs of all sizes land in one pinned array
     per_w, off = {}, 0
     for w, is_fc in WIDTHS:
         idx, rows, cols = offline.blocks_of_images(N_IMAGES, HEIGHT, WIDTH_IMAGE, w)
@@ -265,7 +266,7 @@ def main():
             'h_cols': torch.from_numpy(cols).pin_memory(),
             'd_u8': torch.empty((n, w * w), dtype=torch.uint8, device=dev),
             'h_u8': torch.empty((n, w, w), dtype=torch.uint8).pin_memory(),
-            'h_psnr': torch.empty(n, dtype=torch.float64).pin_memory(),
+            'h_psnr': h_psnr_all[off:off + n],
         }
         for k in ('idx', 'rows', 'cols'):
             per_w[w]['d_' + k] = per_w[w]['h_' + k].to(dev)
@@ -304,15 +305,18 @@ def main():
         return offline.gather_statistics(d_psnr, d_win, rank, world)
 
     def step_e2e():
-        psnrs = []
-        for w, _ in WIDTHS:
+        # smallest block list first: its host-side validation is short, so the GPU starts at once and the validation of
+        # the larger lists overlaps the kernels
+        for w, _ in sorted(WIDTHS, key=lambda wf: per_w[wf[0]]['n']):
             p = per_w[w]
+            # asynchronous form of the host-pointer call: the four block sizes are enqueued back to back, uploads and
+            # read-backs overlap the kernels of the neighbouring size; every output is read after synchronize()
             eng.predict_image_blocks(w, p['is_fc'], images_pin.numpy(), p['h_rows'].numpy(), p['h_cols'].numpy(),
                                      p['h_idx'].numpy(), want_float=False, out_uint8=p['h_u8'].numpy(),
-                                     out_psnr=p['h_psnr'].numpy())
-            psnrs.append(p['h_psnr'])
-        psnr_all = torch.cat(psnrs)
-        wins = (psnr_all - base_host > 0.).to(torch.uint8)
+                                     out_psnr=p['h_psnr'].numpy(), wait=False)
+        eng.synchronize()
+        psnr_all = h_psnr_all
+        wins = psnr_all > base_host                      # = (psnr - baseline > 0), comparing_pnn_ipfcns_hevc_best_mode.py:87
         if world > 1:
             g_psnr, g_win = offline.gather_statistics(psnr_all.to(dev), wins.to(dev), rank, world)
             if rank == 0:

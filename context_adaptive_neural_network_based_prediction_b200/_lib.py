@@ -16,7 +16,7 @@ EXPORTS = (
     'pnn_predict_batch_device', 'pnn_predict_image_blocks_device', 'pnn_launch_count',
     'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation', 'pnn_win_flags_device', 'pnn_set_profiling',
     'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused', 'pnn_hevc_best_mode', 'pnn_hevc_best_mode_device',
-    'pnn_inspect_net_file',
+    'pnn_inspect_net_file', 'pnn_predict_image_blocks_async', 'pnn_synchronize',
 )
 
 PRECISION_FP32 = 0
@@ -57,6 +57,10 @@ def load():
     lib.pnn_predict_batch.restype = i32
     lib.pnn_predict_image_blocks.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp, vp, vp]
     lib.pnn_predict_image_blocks.restype = i32
+    lib.pnn_predict_image_blocks_async.argtypes = lib.pnn_predict_image_blocks.argtypes
+    lib.pnn_predict_image_blocks_async.restype = i32
+    lib.pnn_synchronize.argtypes = [vp]
+    lib.pnn_synchronize.restype = i32
     lib.pnn_predict_batch_device.argtypes = [vp, i32, i32, vp, vp, i64, vp, vp]
     lib.pnn_predict_batch_device.restype = i32
     lib.pnn_predict_image_blocks_device.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32,

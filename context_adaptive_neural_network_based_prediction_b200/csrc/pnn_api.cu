@@ -121,11 +121,18 @@ struct Net {
     int hm_exec_precision = -1;
     int hm_launches = 0;
     DevBuf hm_vec[3];
+    // asynchronous read-back of the image-block path (stream_out) still reading out_* of this net
+    cudaEvent_t computed = nullptr, read_back = nullptr;
+    bool read_back_pending = false;
     void drop_hm_graph() {
         if (hm_exec) cudaGraphExecDestroy(hm_exec);
         hm_exec = nullptr;
     }
-    ~Net() { drop_hm_graph(); }
+    ~Net() {
+        drop_hm_graph();
+        if (computed) cudaEventDestroy(computed);
+        if (read_back) cudaEventDestroy(read_back);
+    }
 };
 
 FlatFile read_flat(const std::string& path) {
@@ -457,6 +464,15 @@ struct pnn_handle {
     size_t workspace_budget = (size_t)8 << 30;
     // host-API staging
     DevBuf d_images, d_idx, d_rows, d_cols, d_in0, d_in1;
+    // image-block host path: copies run on their own streams so that the upload of call k+1 and the read-back of call k
+    // overlap the kernels of the other call (pnn_predict_image_blocks_async); two input sets alternate
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    struct InputSet {
+        DevBuf images, idx, rows, cols;
+        cudaEvent_t uploaded = nullptr, consumed = nullptr;
+        bool used = false;
+    } in_set[2];
+    int in_next = 0;
     // HM path
     int32_t* hm_staged = nullptr;    // pinned, header + 5*64*64 ints
     int32_t* hm_out = nullptr;       // pinned, 64*64 ints
@@ -786,6 +802,12 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
         h->device = device;
         h->mean = mean_training;
         CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+        for (auto& set : h->in_set) {
+            CUDA_TRY(cudaEventCreateWithFlags(&set.uploaded, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&set.consumed, cudaEventDisableTiming));
+        }
         CUDA_TRY(cudaEventCreate(&h->ev0));
         CUDA_TRY(cudaEventCreate(&h->ev1));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t), cudaHostAllocMapped));
@@ -877,6 +899,12 @@ void pnn_destroy(pnn_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream_in) cudaStreamDestroy(h->stream_in);
+    if (h->stream_out) cudaStreamDestroy(h->stream_out);
+    for (auto& set : h->in_set) {
+        if (set.uploaded) cudaEventDestroy(set.uploaded);
+        if (set.consumed) cudaEventDestroy(set.consumed);
+    }
     delete h;
 }
 
@@ -1443,9 +1471,9 @@ int pnn_predict_image_blocks_device(pnn_handle* h, int width, int is_fc, const u
     return 0;
 }
 
-int pnn_predict_image_blocks(pnn_handle* h, int width, int is_fc, const uint8_t* images, int n_images, int height,
+static int image_blocks_host(pnn_handle* h, int width, int is_fc, const uint8_t* images, int n_images, int height,
                              int width_image, const int32_t* idx, const int32_t* rows, const int32_t* cols, int64_t n,
-                             int mask_w, int mask_h, float* out_f32, uint8_t* out_u8, double* out_psnr) {
+                             int mask_w, int mask_h, float* out_f32, uint8_t* out_u8, double* out_psnr, bool wait) {
     if (!h) return -1;
     try {
         if (n < 0) throw std::runtime_error("negative number of predictions");
@@ -1468,30 +1496,84 @@ int pnn_predict_image_blocks(pnn_handle* h, int width, int is_fc, const uint8_t*
         const int64_t px = (int64_t)width * width;
         cudaStream_t s = h->stream;
         const size_t img_bytes = (size_t)n_images * height * width_image;
-        h->d_images.reserve(img_bytes);
-        h->d_rows.reserve(n * 4);
-        h->d_cols.reserve(n * 4);
-        if (idx) h->d_idx.reserve(n * 4);
-        CUDA_TRY(cudaMemcpyAsync(h->d_images.p, images, img_bytes, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(h->d_rows.p, rows, n * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(h->d_cols.p, cols, n * 4, cudaMemcpyHostToDevice, s));
-        if (idx) CUDA_TRY(cudaMemcpyAsync(h->d_idx.p, idx, n * 4, cudaMemcpyHostToDevice, s));
+        // upload on stream_in into the input set that the call before the previous one used
+        pnn_handle::InputSet& in = h->in_set[h->in_next];
+        h->in_next ^= 1;
+        in.images.reserve(img_bytes);          // growing frees the old buffer, which waits for the device
+        in.rows.reserve(n * 4);
+        in.cols.reserve(n * 4);
+        if (idx) in.idx.reserve(n * 4);
+        if (in.used) CUDA_TRY(cudaStreamWaitEvent(h->stream_in, in.consumed, 0));
+        CUDA_TRY(cudaMemcpyAsync(in.images.p, images, img_bytes, cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(in.rows.p, rows, n * 4, cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaMemcpyAsync(in.cols.p, cols, n * 4, cudaMemcpyHostToDevice, h->stream_in));
+        if (idx) CUDA_TRY(cudaMemcpyAsync(in.idx.p, idx, n * 4, cudaMemcpyHostToDevice, h->stream_in));
+        CUDA_TRY(cudaEventRecord(in.uploaded, h->stream_in));
+        CUDA_TRY(cudaStreamWaitEvent(s, in.uploaded, 0));
         // outputs are produced chunk by chunk into the net's own output buffers
         const int64_t cap = choose_capacity(h, net, n);
         ensure_workspace(net, cap);
+        if (!net.computed) {
+            CUDA_TRY(cudaEventCreateWithFlags(&net.computed, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&net.read_back, cudaEventDisableTiming));
+        }
+        if (net.read_back_pending) CUDA_TRY(cudaStreamWaitEvent(s, net.read_back, 0));   // out_* still being read
         for (int64_t s0 = 0; s0 < n; s0 += cap) {
             const int64_t m = std::min(cap, n - s0);
-            image_blocks_device(h, net, (const uint8_t*)h->d_images.p, height, width_image,
-                                idx ? (const int32_t*)h->d_idx.p + s0 : nullptr, (const int32_t*)h->d_rows.p + s0,
-                                (const int32_t*)h->d_cols.p + s0, m, mask_w, mask_h,
+            const bool last = s0 + cap >= n;
+            image_blocks_device(h, net, (const uint8_t*)in.images.p, height, width_image,
+                                idx ? (const int32_t*)in.idx.p + s0 : nullptr, (const int32_t*)in.rows.p + s0,
+                                (const int32_t*)in.cols.p + s0, m, mask_w, mask_h,
                                 out_f32 ? (float*)net.out_raw.p : nullptr,
                                 (out_u8 || out_psnr) ? (uint8_t*)net.out_u8.p : nullptr,
                                 out_psnr ? (double*)net.out_psnr.p : nullptr, s);
-            if (out_f32) CUDA_TRY(cudaMemcpyAsync(out_f32 + s0 * px, net.out_raw.p, (size_t)m * px * 4, cudaMemcpyDeviceToHost, s));
-            if (out_u8) CUDA_TRY(cudaMemcpyAsync(out_u8 + s0 * px, net.out_u8.p, (size_t)m * px, cudaMemcpyDeviceToHost, s));
-            if (out_psnr) CUDA_TRY(cudaMemcpyAsync(out_psnr + s0, net.out_psnr.p, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
+            // the read-back of the last chunk goes to stream_out (it overlaps the next call); earlier chunks stay in order
+            cudaStream_t so = s;
+            if (last) {
+                CUDA_TRY(cudaEventRecord(net.computed, s));
+                CUDA_TRY(cudaStreamWaitEvent(h->stream_out, net.computed, 0));
+                so = h->stream_out;
+            }
+            if (out_f32) CUDA_TRY(cudaMemcpyAsync(out_f32 + s0 * px, net.out_raw.p, (size_t)m * px * 4, cudaMemcpyDeviceToHost, so));
+            if (out_u8) CUDA_TRY(cudaMemcpyAsync(out_u8 + s0 * px, net.out_u8.p, (size_t)m * px, cudaMemcpyDeviceToHost, so));
+            if (out_psnr) CUDA_TRY(cudaMemcpyAsync(out_psnr + s0, net.out_psnr.p, (size_t)m * 8, cudaMemcpyDeviceToHost, so));
         }
+        CUDA_TRY(cudaEventRecord(net.read_back, h->stream_out));
+        net.read_back_pending = true;
+        CUDA_TRY(cudaEventRecord(in.consumed, s));
+        in.used = true;
+        if (wait) {
+            CUDA_TRY(cudaStreamSynchronize(h->stream_out));   // ordered after the kernels of this call
+            net.read_back_pending = false;
+        }
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_image_blocks(pnn_handle* h, int width, int is_fc, const uint8_t* images, int n_images, int height,
+                             int width_image, const int32_t* idx, const int32_t* rows, const int32_t* cols, int64_t n,
+                             int mask_w, int mask_h, float* out_f32, uint8_t* out_u8, double* out_psnr) {
+    return image_blocks_host(h, width, is_fc, images, n_images, height, width_image, idx, rows, cols, n, mask_w, mask_h, out_f32,
+                             out_u8, out_psnr, true);
+}
+
+int pnn_predict_image_blocks_async(pnn_handle* h, int width, int is_fc, const uint8_t* images, int n_images, int height,
+                                   int width_image, const int32_t* idx, const int32_t* rows, const int32_t* cols, int64_t n,
+                                   int mask_w, int mask_h, float* out_f32, uint8_t* out_u8, double* out_psnr) {
+    return image_blocks_host(h, width, is_fc, images, n_images, height, width_image, idx, rows, cols, n, mask_w, mask_h, out_f32,
+                             out_u8, out_psnr, false);
+}
+
+int pnn_synchronize(pnn_handle* h) {
+    if (!h) return -1;
+    try {
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaStreamSynchronize(h->stream_in));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream_out));
+        for (auto& kv : h->nets) kv.second->read_back_pending = false;
     } catch (const std::exception& e) {
         return fail(h, e);
     }

@@ -37,6 +37,7 @@ class Engine(object):
     def __init__(self, mean_training=MEAN_TRAINING_LUMINANCE, device=0, paths_file=None, qp_selection=22):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
+        self._pending = []                      # arrays of enqueued asynchronous calls, kept alive until synchronize()
         self.mean_training = float(mean_training)
         path = paths_file.encode() if paths_file else None
         if self._lib.pnn_create(path, ctypes.c_float(self.mean_training), int(qp_selection), int(device),
@@ -132,11 +133,15 @@ class Engine(object):
 
     def predict_image_blocks(self, width_target, is_fully_connected, images_uint8, rows, cols, image_index=None,
                              masks=(0, 0), want_float=True, want_uint8=True, want_psnr=True,
-                             out_float=None, out_uint8=None, out_psnr=None):
+                             out_float=None, out_uint8=None, out_psnr=None, wait=True):
         """Fused gather + net + epilogue for blocks of uint8 images [n_images, H, W_img] (or [H, W_img]).
 
         Returns a dict with 'predictions_float32' [N, W, W] (raw), 'predictions_uint8' [N, W, W] and
         'psnrs' [N] (float64) for the requested outputs.
+
+        `wait=False` (C ABI pnn_predict_image_blocks_async) returns once the work is enqueued: uploads, kernels and
+        read-backs of successive calls overlap, the outputs are complete after `synchronize()` (pass pinned arrays for
+        real overlap; do not modify the inputs before `synchronize()`).
         """
         img = numpy.ascontiguousarray(images_uint8, dtype=numpy.uint8)
         if img.ndim == 2:
@@ -153,7 +158,11 @@ class Engine(object):
         for arr, dt, count in ((f32, numpy.float32, n * w * w), (u8, numpy.uint8, n * w * w), (psnr, numpy.float64, n)):
             if arr is not None and (arr.dtype != dt or arr.size != count or not arr.flags['C_CONTIGUOUS']):
                 raise ValueError('an output array has the wrong dtype, size or layout')
-        self._check(self._lib.pnn_predict_image_blocks(
+        if not wait:
+            # the arrays the library reads and writes after this call returns stay referenced until synchronize()
+            self._pending.append((img, rows, cols, idx, f32, u8, psnr))
+        call = self._lib.pnn_predict_image_blocks if wait else self._lib.pnn_predict_image_blocks_async
+        self._check(call(
             self._h, w, int(bool(is_fully_connected)), _ptr(img), img.shape[0], img.shape[1], img.shape[2],
             _ptr(idx), _ptr(rows), _ptr(cols), n, int(masks[0]), int(masks[1]), _ptr(f32), _ptr(u8), _ptr(psnr)))
         out = {}
@@ -164,6 +173,11 @@ class Engine(object):
         if psnr is not None:
             out['psnrs'] = psnr
         return out
+
+    def synchronize(self):
+        """Waits for the calls made with `wait=False` (C ABI pnn_synchronize)."""
+        self._check(self._lib.pnn_synchronize(self._h))
+        self._pending = []
 
     def hevc_best_mode(self, width_target, images_uint8, rows, cols, image_index=None, masks=(0, 0), want_predictions=True):
         """Best of the 35 HEVC intra modes per block (reference hevc/intraprediction/intraprediction.py:183-292).

@@ -21,6 +21,9 @@ ap.add_argument('--seed', type=int, default=0)
 ap.add_argument('--image', default='', help='.npy uint8 luminance image instead of the synthetic frame')
 ap.add_argument('--trained-small-nets', action='store_true',
                 help='widths 4 and 8 use the two pretrained checkpoints the reference ships (CONV-4, CONV-8, tests/golden/)')
+ap.add_argument('--frozen-graphs', action='store_true',
+                help='the paths file names frozen graphs (binary GraphDef `graph_output.pbtxt`, as the reference HM set-up has them) '
+                     'instead of PNNW files: libpnn_cuda reads their constants itself')
 args = ap.parse_args()
 
 build = os.path.join(ROOT, 'hm', '_build')
@@ -36,6 +39,13 @@ for w, is_fc in ((4, True), (8, True), (16, False), (32, False), (64, False)):
         path = os.path.join(ROOT, 'tests', 'golden', 'conv%d_single.pnnw' % w)
     else:
         weights.save_flat(path, w, is_fc, weights.init_weights(w, is_fc, seed=w))
+    if args.frozen_graphs:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        from test_weights_export_cpu import make_graph          # GraphDef encoder of the tests
+        width_f, is_fc_f, wts = weights.load_flat(path)
+        os.makedirs(os.path.join(tmp, 'graph_%d' % w), exist_ok=True)
+        path = os.path.join(tmp, 'graph_%d' % w, 'graph_output.pbtxt')
+        make_graph(path, wts, width_f, bool(is_fc_f))
     lines += ['%d,0,0,%s' % (w, path), '%d,1,0,%s' % (w, path)]
 paths_file = os.path.join(tmp, 'paths.txt')
 open(paths_file, 'w').write('\n'.join(lines) + '\n')

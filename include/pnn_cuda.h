@@ -134,6 +134,21 @@ int pnn_predict_image_blocks(pnn_handle* h, int width, int is_fully_connected,
                              int mask_w, int mask_h, float* out_f32, uint8_t* out_u8, double* out_psnr);
 
 /*
+ * Asynchronous form of pnn_predict_image_blocks for callers that evaluate several block sizes (or several image sets)
+ * back to back, as comparing_pnn_ipfcns_hevc_best_mode.py:220-322 does per width: the call returns once the work is
+ * enqueued; uploads, kernels and read-backs run on three streams, so the upload of call k+1 and the read-back of call k
+ * overlap the kernels of the other call.  The host buffers (inputs AND outputs) must stay valid, and should be pinned,
+ * until pnn_synchronize returns; outputs are complete only then.  Same arguments and checks as the synchronous call.
+ */
+int pnn_predict_image_blocks_async(pnn_handle* h, int width_target, int is_fully_connected, const uint8_t* images_uint8,
+                                   int n_images, int height, int width_image, const int32_t* image_index,
+                                   const int32_t* rows, const int32_t* cols, int64_t n, int mask_w, int mask_h,
+                                   float* out_float32, uint8_t* out_uint8, double* out_psnr);
+
+/* Waits for everything enqueued on the handle (pnn_predict_image_blocks_async). */
+int pnn_synchronize(pnn_handle* h);
+
+/*
  * Same two calls with DEVICE pointers, asynchronous on `cuda_stream` (a cudaStream_t, may be 0).
  * These are what the throughput numbers with inputs resident in HBM are measured on.
  */

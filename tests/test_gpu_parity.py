@@ -161,3 +161,26 @@ def test_shim_entry_points(weights_dir):
         batching.predict_by_batch_via_pnn((flat[:33],), None, predictor, 10)
     conv = PredictionNeuralNetwork(10, 16, False)
     assert conv.strides_branch == (2, 1, 2, 1) and conv.is_fully_connected is False
+
+
+@pytest.mark.gpu
+def test_async_image_blocks_equal_sync(engine, weights_dir):
+    """pnn_predict_image_blocks_async + pnn_synchronize: same bits as the synchronous call, several calls in flight
+    (two widths, the same width twice, more calls than input sets)."""
+    images = numpy.stack([helpers.synthetic_image(96, 160, s) for s in range(3)])
+    jobs = []
+    for width, is_fc in ((4, True), (16, False), (4, True), (8, True), (16, False)):
+        path, _ = helpers.make_net_file(weights_dir, width, is_fc, seed=width)
+        engine.load_net(path)
+        rows, cols = helpers.grid_blocks(96, 160, width)
+        rows, cols = numpy.tile(rows, 3), numpy.tile(cols, 3)
+        idx = numpy.repeat(numpy.arange(3, dtype=numpy.int32), len(rows) // 3)
+        if len(jobs) == 2:                                  # a different block list for the repeated width
+            rows, cols, idx = rows[::2].copy(), cols[::2].copy(), idx[::2].copy()
+        jobs.append((width, is_fc, rows, cols, idx))
+    sync = [engine.predict_image_blocks(w, fc, images, r, c, i) for w, fc, r, c, i in jobs]
+    asyn = [engine.predict_image_blocks(w, fc, images, r, c, i, wait=False) for w, fc, r, c, i in jobs]
+    engine.synchronize()
+    for a, b in zip(sync, asyn):
+        for key in ('predictions_float32', 'predictions_uint8', 'psnrs'):
+            numpy.testing.assert_array_equal(a[key], b[key])
