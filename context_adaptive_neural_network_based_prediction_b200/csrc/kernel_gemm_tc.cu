@@ -23,11 +23,12 @@
 //   warp 5     TMEM allocation (512 columns = two accumulators) + single-thread MMA issue;
 //              tcgen05.commit frees the smem stage / publishes the accumulator.
 //   warps 8-11 / 12-15  two epilogue sets, one per accumulator, so that the epilogues of tiles i and i+1
-//              and the main loop of tile i+2 overlap: tcgen05.ld -> bias -> LeakyReLU -> hi/lo split ->
-//              swizzled staging in shared memory -> 16-byte global stores where 4 consecutive lanes cover
-//              64 contiguous bytes of one row (or the final epilogue: raw fp32 + add-mean / clip / round).
+//              and the main loop of tile i+2 overlap: tcgen05.ld -> bias (warp-uniform 16-byte loads) -> LeakyReLU ->
+//              hi/lo split (packed cvt) -> 32-byte global stores straight from registers, a lane owning the 64 contiguous
+//              bytes per plane of its row in a 32-column block (or the final epilogue: raw fp32 + add-mean / clip / round).
 //   (warps 6-7 idle: they keep the epilogue sets aligned on warpgroups / TMEM lane quarters)
-// The smem ring has 2-4 stages depending on the tile width (A 32 KB + B 2*bn*128 B per stage).
+// The 224 KB smem ring has 2-6 stages depending on the tile width (A 32 KB + B 2*bn*128 B per stage); in tap-reuse mode
+// it is split into an A ring (2-3 x 40 KB) and a B ring (4-8 stages).
 #include "kernels_common.cuh"
 
 #include <cuda.h>
@@ -40,9 +41,8 @@ namespace {
 
 constexpr int MAX_STAGES = 8;
 constexpr int A_PLANE = TC_BM * 128;                 // 16 KB
-constexpr int RING_BYTES = 2 * (2 * A_PLANE + 2 * TC_BN * 128);   // 192 KB: 2 stages at bn = 256, 3 at 128, 4 at <= 64
-constexpr int STAGING_BYTES = 8 * 4096;              // per epilogue warp: 32 rows x 64 B, hi and lo
-constexpr int SMEM_BYTES = RING_BYTES + STAGING_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
+constexpr int RING_BYTES = 224 * 1024;               // 2 stages at bn = 256 (96 KB each), 3 at 128, 4 at 64
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
 constexpr int XR_A_ROWS = 160;                       // tap-reuse box: (8 + 2) x bh x nb rows
 constexpr int XR_A_PLANE = XR_A_ROWS * 128;          // 20 KB
 constexpr int NUM_THREADS = 512;
@@ -143,6 +143,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -203,8 +208,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
     extern __shared__ uint8_t smem_raw[];
     const GemmGeom& g = L.g;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t staging = smem_base + RING_BYTES;
-    const uint32_t bars = staging + STAGING_BYTES;
+    const uint32_t bars = smem_base + RING_BYTES;
     // barrier slots (8 B each)
     auto full_a = [&](int s) { return bars + 8u * s; };
     auto full_b = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
     const bool merged = g.N <= 128;
     // tap-reuse mode: A ring (stages of two 20 KB planes) then B ring
     // (the B ring must be deep: a K block of a narrow layer is ~0.35 us of tensor work against a ~2 us load round trip)
-    const int xr_na = 2, xr_nb = bn_max <= 32 ? 8 : (bn_max <= 64 ? 7 : 3);
+    const int xr_na = bn_max <= 64 ? 3 : 2, xr_nb = bn_max <= 32 ? 8 : (bn_max <= 64 ? 6 : 4);
     const uint32_t xr_b_bytes = 2u * (uint32_t)bn_max * 128u;
     const uint32_t xr_b_base = smem_base + (uint32_t)xr_na * 2u * XR_A_PLANE;
     const int chunks = g.Cin >> 6;
@@ -571,10 +575,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
         // ------------------------------------------------------------------ epilogue warps (set 0: 8..11, set 1: 12..15)
         const int set = (warp - 8) >> 2;                     // = accumulator buffer this set drains
         const int q = warp & 3;                              // TMEM lane quarter this warp may read
-        const uint32_t stg_hi = staging + (uint32_t)(warp - 8) * 4096u;
-        const uint32_t stg_lo = stg_hi + 2048u;
-        const int cchunk = lane & 3;                         // 16-byte chunk of a 64-byte row segment in the copy-out phase
-        const RowStep rs8 = make_row_step(g, 8u);
         const RowStep rs1 = make_row_step(g, 1u);
         int j = 0;                                           // tiles this set has processed
         for (int tile = unit + set * units; tile < num_tiles; tile += 2 * units, ++j) {
@@ -584,8 +584,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
             int bn = g.N - n0;
             bn = bn > TC_BN ? TC_BN : ((bn + 15) & ~15);
             int m_own = mt * TC_BM + q * 32 + lane;           // accumulator row owned in the TMEM-read phase
-            // rows this lane copies out: (lane >> 2) + 8*i of the warp's 32 rows
-            int64_t obase[4];
+            // every lane stores the row it reads from TMEM
             int64_t obase_own = -1;
             if (L.tma) {
                 // box order: row r of the tile = (sample r >> box_shift, y (r >> bw_log2) & (bh - 1), x r & (bw - 1))
@@ -594,30 +593,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
                 rr /= L.x_tiles;
                 const int yt = rr % L.y_tiles, bt = rr / L.y_tiles;
                 const int bw_mask = (1 << L.bw_log2) - 1, bh_mask = (1 << L.bh_log2) - 1;
-                auto locate = [&](int r, RowIter& it) {
-                    it.b = (unsigned)(bt * nb_box + (r >> box_shift));
-                    it.oy = (unsigned)((yt << L.bh_log2) + ((r >> L.bw_log2) & bh_mask));
-                    it.ox = (unsigned)((xt << L.bw_log2) + (r & bw_mask));
-                    return (int)it.b < n_samples;
-                };
+                const int r = q * 32 + lane;
                 RowIter it;
-                m_own = locate(q * 32 + lane, it) ? (int)(it.b * (unsigned)g.P + it.oy * (unsigned)g.OW + it.ox) : L.M;
-                if (L.out_mode == OUT_FINAL && m_own < L.M) obase_own = out_offset(g, it);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) obase[i] = locate(q * 32 + (lane >> 2) + 8 * i, it) ? out_offset(g, it) : -1;
-            } else if (L.out_mode == OUT_FINAL) {
-                if (m_own < L.M) obase_own = out_offset(g, row_init(rs1, (unsigned)m_own));
-            } else {
-                RowIter it = row_init(rs8, (unsigned)(mt * TC_BM + q * 32 + (lane >> 2)));
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int m = mt * TC_BM + q * 32 + (lane >> 2) + 8 * i;
-                    obase[i] = m < L.M ? out_offset(g, it) : -1;
-                    row_advance(rs8, it);
-                }
+                it.b = (unsigned)(bt * nb_box + (r >> box_shift));
+                it.oy = (unsigned)((yt << L.bh_log2) + ((r >> L.bw_log2) & bh_mask));
+                it.ox = (unsigned)((xt << L.bw_log2) + (r & bw_mask));
+                const bool ok = (int)it.b < n_samples && it.ox < (unsigned)g.OW && it.oy * (unsigned)g.OW < (unsigned)g.P;
+                m_own = ok ? (int)(it.b * (unsigned)g.P + it.oy * (unsigned)g.OW + it.ox) : L.M;
+                if (ok) obase_own = out_offset(g, it);
+            } else if (m_own < L.M) {
+                obase_own = out_offset(g, row_init(rs1, (unsigned)m_own));
             }
-            // bias of the first 32-column block: one coalesced load per lane, broadcast by shuffle
-            float bias_next = n0 + lane < g.N ? __ldg(L.bias + n0 + lane) : 0.f;
             mbar_wait(tmem_full(set), (uint32_t)j & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * TC_BN);
@@ -632,11 +618,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
                     for (int jj = 0; jj < 32; ++jj) v[jj] = __float_as_uint(__uint_as_float(v[jj]) + __uint_as_float(v2[jj]));
                 }
                 const int nbase = n0 + c0;
-                const float bias_cur = bias_next;
-                if (c0 + 32 < bn) bias_next = nbase + 32 + lane < g.N ? __ldg(L.bias + nbase + 32 + lane) : 0.f;
-                tmem_ld_wait();
                 int nvalid = g.N - nbase;                    // multiple of 16 by construction
                 if (nvalid > 32) nvalid = 32;
+                // the 32 (or 16) bias values of this block: warp-uniform 16-byte loads (one L1 broadcast each) instead of a
+                // shuffle per output element
+                float bias[32];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float4 b4 = jj * 4 < nvalid ? __ldg((const float4*)(L.bias + nbase) + jj) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    bias[4 * jj] = b4.x; bias[4 * jj + 1] = b4.y; bias[4 * jj + 2] = b4.z; bias[4 * jj + 3] = b4.w;
+                }
+                tmem_ld_wait();
                 if (L.debug_flags & 4) continue;
                 if (split_k > 1) {
                     // raw accumulators of this K slice; bias / activation / split happen in splitk_reduce_kernel
@@ -655,51 +647,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(GemmLaunch L, c
                 if (L.out_mode == OUT_FINAL) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) {
-                        const float bj = __shfl_sync(0xffffffffu, bias_cur, jj);
                         if (jj < nvalid && obase_own >= 0) {
-                            float f = __uint_as_float(v[jj]) + bj;
+                            float f = __uint_as_float(v[jj]) + bias[jj];
                             if (g.leaky) f = leaky_relu(f);
                             final_store(L.fin, obase_own + nbase + jj, f);
                         }
                     }
                     continue;
                 }
-                // bias, LeakyReLU, split, swizzled staging (chunk c of row r at position c ^ ((r >> 1) & 3))
+                // bias, LeakyReLU, hi/lo split, and straight to global memory: a lane owns 64 contiguous bytes per plane of its
+                // row in this block, written as 32-byte sectors (st.global.v8; rows start on multiples of 32 bytes because N
+                // is a multiple of 16).  An earlier version staged the tile in shared memory to get 64-byte runs per 4 lanes;
+                // with 256-bit stores that costs more issue slots than it saves, and these warps are issue bound.
+                if (obase_own >= 0) {
+                    __nv_bfloat16* out_hi = (__nv_bfloat16*)L.out.p0 + obase_own + nbase;
+                    __nv_bfloat16* out_lo = (__nv_bfloat16*)L.out.p1 + obase_own + nbase;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t hi[4], lo[4];
+                    for (int half = 0; half < 2; ++half) {
+                        if (half * 16 < nvalid) {
+                            uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int col = ch * 8 + 2 * jj;
-                        float f0 = __uint_as_float(v[col]) + __shfl_sync(0xffffffffu, bias_cur, col);
-                        float f1 = __uint_as_float(v[col + 1]) + __shfl_sync(0xffffffffu, bias_cur, col + 1);
-                        if (g.leaky) {
-                            f0 = leaky_relu(f0);
-                            f1 = leaky_relu(f1);
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const int col = half * 16 + 2 * jj;
+                                float f0 = __uint_as_float(v[col]) + bias[col];
+                                float f1 = __uint_as_float(v[col + 1]) + bias[col + 1];
+                                if (g.leaky) {
+                                    f0 = leaky_relu(f0);
+                                    f1 = leaky_relu(f1);
+                                }
+                                split_bf16x2(f0, f1, hi[jj], lo[jj]);
+                            }
+                            st_global_v8(out_hi + half * 16, hi);
+                            st_global_v8(out_lo + half * 16, lo);
                         }
-                        split_bf16x2(f0, f1, hi[jj], lo[jj]);
-                    }
-                    const uint32_t off = (uint32_t)lane * 64u + (uint32_t)((ch ^ ((lane >> 1) & 3)) << 4);
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
-                }
-                __syncwarp();
-                // copy out: 4 consecutive lanes write the 64 contiguous bytes of one row segment
-                if (cchunk * 8 < nvalid) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (obase[i] < 0) continue;
-                        const int r = (lane >> 2) + 8 * i;
-                        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((cchunk ^ ((r >> 1) & 3)) << 4);
-                        uint4 h, l;
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(stg_hi + off));
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(stg_lo + off));
-                        const int64_t o = obase[i] + nbase + cchunk * 8;
-                        *(uint4*)((__nv_bfloat16*)L.out.p0 + o) = h;
-                        *(uint4*)((__nv_bfloat16*)L.out.p1 + o) = l;
                     }
                 }
-                __syncwarp();
             }
             // this warp's TMEM reads of the tile are done: hand the accumulator back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
