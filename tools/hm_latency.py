@@ -12,6 +12,7 @@ eng.set_hm_fused(fused)
 if "--prof" in sys.argv: eng.set_profiling(True)
 params = {4: 2998816, 8: 3344464, 16: 1339073, 32: 5622657, 64: 20652545}
 print('%3s %10s %10s %12s %12s' % ('W', 'wall_us', 'device_us', 'GB/s(params)', 'cpu_oracle_us'))
+results = {}
 for width in (4, 8, 16, 32, 64):
     is_fc = width <= 8
     path, wts = helpers.make_net_file(tmp, width, is_fc, seed=width)
@@ -45,3 +46,14 @@ for width in (4, 8, 16, 32, 64):
         cpu_us = (time.perf_counter() - t0) / 20 * 1e6
     d = max(float(numpy.median(dev)) * 1e3, 1e-9)
     print('%3d %10.1f %10.1f %12.1f %12.1f' % (width, wall, d, params[width] * 4 / (d * 1e-6) / 1e9, cpu_us), flush=True)
+    results[width] = (wall, cpu_us)
+if cpu:
+    # Projection for BASELINE.json configs[3] (the TF-CPU build cannot be run): the measured encode of the final build
+    # (profiles/r1_config3_hm_substitution_1080p_final.json, QP 32) with every PNN call charged at the CPU stand-in's
+    # batch-1 latency instead of libpnn_cuda's.
+    calls = {4: 130757, 8: 32288, 16: 7857, 32: 1956, 64: 435}
+    encode_s, pnn_s = 13.66, 6.62
+    cpu_pnn_s = sum(calls[w] * results[w][1] * 1e-6 for w in calls)
+    print('projection, 1080p frame at QP 32, %d host threads: PNN calls on the CPU stand-in %.1f s -> encode %.1f s; '
+          'measured with libpnn_cuda: PNN %.2f s, encode %.2f s; ratio %.1fx'
+          % (os.cpu_count(), cpu_pnn_s, encode_s - pnn_s + cpu_pnn_s, pnn_s, encode_s, (encode_s - pnn_s + cpu_pnn_s) / encode_s))
