@@ -250,27 +250,21 @@ __device__ __forceinline__ void fc_hidden_layer(const float* __restrict__ wbase,
     }
 }
 
-__global__ void __launch_bounds__(256) fc_chain_kernel(FcChainLaunch L) {
+__global__ void __launch_bounds__(256) fc_chain_kernel(const __grid_constant__ FcChainLaunch L) {
     __shared__ __align__(16) float xs[1280];
     __shared__ float red[64][17];
     const unsigned long long nb = gridDim.x;
-    const unsigned long long base = (L.seq - 1ULL) * 4ULL * nb;
-    // stage the context: mapped pinned host memory -> device memory (CTA 0 only: one PCIe round trip)
-    if (blockIdx.x == 0) {
-        const int n = HM_HEADER_INTS + 5 * L.W * L.W;
-        for (int i = threadIdx.x; i < n; i += 256) L.staged_dev[i] = L.staged_host[i];
-    }
-    fc_grid_barrier(L.counters, base + 1ULL * nb);
-    for (int k = threadIdx.x; k < L.K[0]; k += 256) xs[k] = hm_context_value(L.staged_dev, L.W, L.mean, k);
+    const unsigned long long base = (L.seq - 1ULL) * 3ULL * nb;
+    for (int k = threadIdx.x; k < L.K[0]; k += 256) xs[k] = L.ctx[k];      // constant bank (kernel parameters)
     __syncthreads();
     fc_hidden_layer(L.w[0], L.bias[0], L.K[0], L.N[0], xs, red, L.vec[0]);
     for (int layer = 1; layer < 3; ++layer) {
-        fc_grid_barrier(L.counters, base + (unsigned long long)(layer + 1) * nb);
+        fc_grid_barrier(L.counters, base + (unsigned long long)layer * nb);
         for (int k = threadIdx.x; k < L.K[layer]; k += 256) xs[k] = __ldcg(L.vec[layer - 1] + k);
         __syncthreads();
         fc_hidden_layer(L.w[layer], L.bias[layer], L.K[layer], L.N[layer], xs, red, L.vec[layer]);
     }
-    fc_grid_barrier(L.counters, base + 4ULL * nb);
+    fc_grid_barrier(L.counters, base + 3ULL * nb);
     // last layer: one warp per output (8 per CTA), weights [N][K]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + warp;

@@ -1278,8 +1278,30 @@ static void run_hm_fc_fused(pnn_handle* h, Net& net) {
         L.N[layer] = st.g.N;
         ++layer;
     }
-    L.staged_host = h->d_hm_staged_mapped;
-    L.staged_dev = (int32_t*)h->d_hm_staged.p;
+    // the context of this call, pre-processed exactly as hm_context_value does on the device (same fp32 operations)
+    {
+        const int32_t* staged = h->hm_staged;
+        const int W = net.W, na = 3 * W * W, total = 5 * W * W;
+        for (int e = 0; e < total; ++e) {
+            float v;
+            if (staged[2] == 0) {
+                memcpy(&v, staged + HM_HEADER_INTS + e, sizeof(float));      // float mode: already pre-processed
+            } else {
+                v = (float)staged[HM_HEADER_INTS + e] - h->mean;
+                if (e < na) {
+                    const int cc = e % (3 * W);
+                    if (cc >= W) {
+                        const int u = (cc - W) / staged[2];
+                        const uint32_t bit = u < 32 ? ((uint32_t)staged[0] >> u) & 1u : ((uint32_t)staged[1] >> (u - 32)) & 1u;
+                        if (!bit) v = 0.f;
+                    }
+                } else if ((e - na) / W >= staged[3]) {
+                    v = 0.f;
+                }
+            }
+            L.ctx[e] = v;
+        }
+    }
     for (int i = 0; i < 3; ++i) L.vec[i] = (float*)net.hm_vec[i].p;
     L.fin.i32 = h->d_hm_out_mapped;
     L.fin.raw = h->d_hm_out_raw_mapped;

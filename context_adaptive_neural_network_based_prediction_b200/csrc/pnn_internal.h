@@ -214,8 +214,10 @@ struct FcChainLaunch {
     const float* w[4];               // [K][N] fp32; w[3] is transposed to [N][K]
     const float* bias[4];
     int K[4], N[4];
-    const int32_t* staged_host;      // device alias of the mapped pinned staging buffer (header + pixels)
-    int32_t* staged_dev;
+    // The pre-processed context (mean-centred, masked; 80 or 320 floats) travels IN the kernel parameters: the launch
+    // packet carries it to the GPU, so no CTA reads host memory over PCIe and the grid barrier that published the staged
+    // copy is gone (4 -> 3 barriers per call).
+    float ctx[320];
     float* vec[3];
     FinalOut fin;                    // mapped pinned outputs
     unsigned long long* counters;    // [0] grid-barrier arrivals, [1] completions (monotonic)
