@@ -480,11 +480,13 @@ struct pnn_handle {
     float* hm_out_raw = nullptr;             // pinned + mapped, 64*64 floats (raw prediction)
     float* d_hm_out_raw_mapped = nullptr;
     int32_t* d_hm_staged_mapped = nullptr;   // device alias of hm_staged
-    volatile int* hm_flag = nullptr;         // pinned + mapped completion flag of the fused FC kernel
+    volatile uint64_t* hm_ll = nullptr;      // pinned + mapped {value, seq} pairs written by the fused FC kernel
+    uint2* d_hm_ll_mapped = nullptr;
+    volatile int* hm_flag = nullptr;         // pinned + mapped completion flag (unused by the current fused kernel)
     int* d_hm_flag_mapped = nullptr;
     DevBuf d_splitk;                         // split-K partial sums of the in-loop conv calls
-    DevBuf d_fc_counters;
-    unsigned long long fc_seq = 0;
+    DevBuf d_fc_counters, d_fc_xchg, d_fc_stamps;
+    unsigned long long fc_seq = 0, fc_done_total = 0;
     bool hm_fused_fc = true;
     bool hm_split_k = true;
     DevBuf d_hm_staged;
@@ -896,6 +898,7 @@ void pnn_destroy(pnn_handle* h) {
     if (h->hm_out) cudaFreeHost(h->hm_out);
     if (h->hm_out_raw) cudaFreeHost(h->hm_out_raw);
     if (h->hm_flag) cudaFreeHost((void*)h->hm_flag);
+    if (h->hm_ll) cudaFreeHost((void*)h->hm_ll);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1302,14 +1305,25 @@ static void run_hm_fc_fused(pnn_handle* h, Net& net) {
             L.ctx[e] = v;
         }
     }
-    for (int i = 0; i < 3; ++i) L.vec[i] = (float*)net.hm_vec[i].p;
-    L.fin.i32 = h->d_hm_out_mapped;
-    L.fin.raw = h->d_hm_out_raw_mapped;
+    if (!h->d_fc_xchg.p) {
+        h->d_fc_xchg.reserve(3 * 1280 * sizeof(uint2));
+        CUDA_TRY(cudaMemset(h->d_fc_xchg.p, 0, 3 * 1280 * sizeof(uint2)));
+    }
+    L.xchg = (uint2*)h->d_fc_xchg.p;
+    if (!h->hm_ll) {
+        CUDA_TRY(cudaHostAlloc((void**)&h->hm_ll, 128 * sizeof(uint2), cudaHostAllocMapped));
+        memset((void*)h->hm_ll, 0, 128 * sizeof(uint2));
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_ll_mapped, (void*)h->hm_ll, 0));
+    }
+    L.out_ll = h->d_hm_ll_mapped;
     L.fin.mean = h->mean;
     L.fin.round_mode = PNN_ROUND_HALF_AWAY;
-    L.counters = (unsigned long long*)h->d_fc_counters.p;
     L.seq = ++h->fc_seq;
-    L.done_flag = (volatile int*)h->d_hm_flag_mapped;
+    static const bool want_stamps = getenv("PNN_FC_STAMPS") && atoi(getenv("PNN_FC_STAMPS")) != 0;
+    if (want_stamps) {
+        if (!h->d_fc_stamps.p) h->d_fc_stamps.reserve(16 * sizeof(unsigned long long));
+        L.stamps = (unsigned long long*)h->d_fc_stamps.p;
+    }
     L.W = net.W;
     L.mean = h->mean;
     cudaStream_t s = h->stream;
@@ -1317,18 +1331,37 @@ static void run_hm_fc_fused(pnn_handle* h, Net& net) {
     h->launches += launch_fc_chain(L, s);
     if (h->profiling) CUDA_TRY(cudaEventRecord(h->ev1, s));
     CUDA_TRY(cudaGetLastError());
-    // spin on the mapped flag; fall back to the stream to surface an error if it never comes
-    const int want = (int)L.seq;
+    // every output arrives as an 8-byte {value, seq} pair in mapped memory: poll them (aligned 8-byte reads are atomic);
+    // fall back to the stream to surface an error if they never come
+    const uint32_t want = (uint32_t)L.seq;
+    const int n_out = L.N[3];
     long long spins = 0;
-    while (*h->hm_flag != want) {
-        if (++spins > 200000000LL) {
-            CUDA_TRY(cudaStreamSynchronize(s));
-            if (*h->hm_flag != want) throw std::runtime_error("the fused FC kernel did not complete");
+    for (int n = 0; n < n_out; ++n) {
+        for (;;) {
+            const uint64_t a = h->hm_ll[n], b = h->hm_ll[64 + n];
+            if ((uint32_t)(a >> 32) == want && (uint32_t)(b >> 32) == want) {
+                const uint32_t raw_bits = (uint32_t)a;
+                memcpy(h->hm_out_raw + n, &raw_bits, sizeof(float));
+                h->hm_out[n] = (int32_t)(uint32_t)b;
+                break;
+            }
+            if (++spins > 200000000LL) {
+                CUDA_TRY(cudaStreamSynchronize(s));
+                throw std::runtime_error("the fused FC kernel did not complete");
+            }
         }
     }
     if (h->profiling) {
         CUDA_TRY(cudaStreamSynchronize(s));
         CUDA_TRY(cudaEventElapsedTime(&h->hm_ms, h->ev0, h->ev1));
+    }
+    if (want_stamps && (L.seq % 1000) == 0) {
+        unsigned long long t[8];
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaMemcpy(t, h->d_fc_stamps.p, sizeof(t), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "fc_chain W=%d stamps (ns since kernel start; layer / exchange x3, last layer):", net.W);
+        for (int i = 1; i < 8; ++i) fprintf(stderr, " %lld", (long long)(t[i] - t[0]));
+        fprintf(stderr, "\n");
     }
 }
 

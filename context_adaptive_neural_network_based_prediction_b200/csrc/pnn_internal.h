@@ -218,15 +218,15 @@ struct FcChainLaunch {
     // packet carries it to the GPU, so no CTA reads host memory over PCIe and the grid barrier that published the staged
     // copy is gone (4 -> 3 barriers per call).
     float ctx[320];
-    float* vec[3];
-    FinalOut fin;                    // mapped pinned outputs
-    unsigned long long* counters;    // [0] grid-barrier arrivals, [1] completions (monotonic)
+    uint2* xchg;                     // [3 layers][1280] {value bits, tag} pairs (zero-initialised once)
+    FinalOut fin;                    // mean and rounding mode of the output epilogue
+    uint2* out_ll;                   // mapped pinned host memory: [64] {raw bits, seq} then [64] {rounded int, seq}
     unsigned long long seq;          // 1, 2, 3, ... per call
-    volatile int* done_flag;         // device alias of the mapped pinned completion flag
+    unsigned long long* stamps;      // tuning aid (PNN_FC_STAMPS=1): %globaltimer of CTA 0 at 10 points, or NULL
     int W;
     float mean;
 };
-constexpr int FC_CHAIN_CTAS = 75;    // 1200 hidden units / 16 columns per CTA
+constexpr int FC_CHAIN_CTAS = 150;   // 1200 hidden units / 8 columns per CTA (two CTAs on two of the 148 SMs)
 int launch_fc_chain(const FcChainLaunch& L, cudaStream_t stream);
 void small_kernels_init();
 
