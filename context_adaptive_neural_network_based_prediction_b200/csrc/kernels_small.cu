@@ -377,8 +377,7 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
 }
 
 template <int K, int S, bool SPLIT, int CG, int PR>
-__global__ void __launch_bounds__(CF_THREADS, PR == 4 ? 3 : 5) conv_first_kernel(const __grid_constant__ ConvFirstLaunch L,
-                                                                                 const __grid_constant__ ConvFirstWeights Wt) {
+__device__ __forceinline__ void conv_first_body(const ConvFirstLaunch& L, const ConvFirstWeights& Wt) {
     const unsigned OW = (unsigned)L.OW, groups = (unsigned)L.OH / PR;
     const int64_t total = (int64_t)L.n * groups * OW;
     constexpr int NR = (PR - 1) * S + K;                           // input rows feeding PR output rows
@@ -447,8 +446,31 @@ __global__ void __launch_bounds__(CF_THREADS, PR == 4 ? 3 : 5) conv_first_kernel
     }
 }
 
+template <int K, int S, bool SPLIT, int CG, int PR>
+__global__ void __launch_bounds__(CF_THREADS, PR == 4 ? 3 : 5) conv_first_kernel(const __grid_constant__ ConvFirstLaunch L,
+                                                                                 const __grid_constant__ ConvFirstWeights Wt) {
+    conv_first_body<K, S, SPLIT, CG, PR>(L, Wt);
+}
+
+// Batch-1 (in-loop) calls: all channel groups in ONE launch, group = blockIdx.y.  At this size the instruction-fetch
+// stalls of the switch do not matter and three launches per branch are saved.
+template <int K, int S, bool SPLIT, int PR>
+__global__ void __launch_bounds__(CF_THREADS, PR == 4 ? 3 : 5) conv_first_all_groups_kernel(const __grid_constant__ ConvFirstLaunch L,
+                                                                                            const __grid_constant__ ConvFirstWeights Wt) {
+    switch (blockIdx.y) {
+        case 0: conv_first_body<K, S, SPLIT, 0, PR>(L, Wt); break;
+        case 1: conv_first_body<K, S, SPLIT, 1, PR>(L, Wt); break;
+        case 2: conv_first_body<K, S, SPLIT, 2, PR>(L, Wt); break;
+        default: conv_first_body<K, S, SPLIT, 3, PR>(L, Wt); break;
+    }
+}
+
 template <int K, int S, bool SPLIT, int PR>
 void conv_first_launch_groups(const ConvFirstLaunch& L, const ConvFirstWeights& W, unsigned grid, cudaStream_t stream) {
+    if (grid <= 148) {
+        conv_first_all_groups_kernel<K, S, SPLIT, PR><<<dim3(grid, L.C / 16), CF_THREADS, 0, stream>>>(L, W);
+        return;
+    }
     conv_first_kernel<K, S, SPLIT, 0, PR><<<grid, CF_THREADS, 0, stream>>>(L, W);
     conv_first_kernel<K, S, SPLIT, 1, PR><<<grid, CF_THREADS, 0, stream>>>(L, W);
     if (L.C == 64) {
@@ -469,7 +491,7 @@ int launch_conv_first(const ConvFirstLaunch& L, const ConvFirstWeights& W, cudaS
         if (L.split) conv_first_launch_groups<3, 1, true, PR>(L, W, grid, stream);
         else conv_first_launch_groups<3, 1, false, PR>(L, W, grid, stream);
     }
-    return L.C / 16;
+    return grid <= 148 ? 1 : L.C / 16;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -776,6 +798,23 @@ __global__ void __launch_bounds__(MG5_THREADS, 2) merger_mma_kernel(MergerLaunch
     }
 }
 
+// In-loop (batch-1) merger: thread = (sample, output o, channel c), c fastest, 80-term fp32 dot product in fixed order.
+// For one sample the tensor-core kernel spends its 21 us preparing 80 KB of weight fragments per CTA; this one reads the
+// 80*16*C weights once, coalesced.
+__global__ void __launch_bounds__(256) merger_small_kernel(MergerLaunch L) {
+    const int C = L.C;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= L.n * 16 * C) return;
+    const int c = idx % C, o = (idx / C) & 15, s = idx / (16 * C);
+    float acc = 0.f;
+    const int64_t b0 = (int64_t)s * 48 * C + c, b1 = (int64_t)s * 32 * C + c;
+#pragma unroll 8
+    for (int q = 0; q < 48; ++q) acc = fmaf(act_load<true>(L.in0, b0 + (int64_t)q * C), __ldg(L.w + ((int64_t)q * 16 + o) * C + c), acc);
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) acc = fmaf(act_load<true>(L.in1, b1 + (int64_t)q * C), __ldg(L.w + ((int64_t)(48 + q) * 16 + o) * C + c), acc);
+    act_store<true>(L.out, ((int64_t)s * 16 + o) * C + c, leaky_relu(acc + __ldg(L.bias + (int64_t)o * C + c)));
+}
+
 int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
     if (L.n == 0) return 0;
     if (L.C % MG_CH) return -1;
@@ -784,6 +823,10 @@ int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
         cudaFuncSetAttribute(merger_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
         cudaFuncSetAttribute(merger_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
         g_merger_init = 1;
+    }
+    if (L.split && L.in_loop) {
+        merger_small_kernel<<<(L.n * 16 * L.C + 255) / 256, 256, 0, stream>>>(L);
+        return 1;
     }
     static const int use_mma = getenv("PNN_MERGER_MMA") ? atoi(getenv("PNN_MERGER_MMA")) != 0 : 1;
     if (L.split && use_mma) {

@@ -635,6 +635,7 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.w = st.d_w32;
                 L.bias = st.d_bias;
                 L.n = (int)n; L.C = st.C; L.split = split;
+                L.in_loop = allow_split_k ? 1 : 0;
                 ProfScope ps(h, stream, "merger", n * st.C, 16, 80, false);
                 h->launches += launch_merger(L, stream);
                 break;

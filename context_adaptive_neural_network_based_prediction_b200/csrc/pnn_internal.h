@@ -153,6 +153,7 @@ struct MergerLaunch {
     const float* w;      // transposed on the host to [80][16][C]
     const float* bias;   // [16][C]
     int n, C, split;
+    int in_loop;         // 1: batch-1 call of the codec (fp32 direct kernel; the batched paths keep one arithmetic for every n)
 };
 int launch_merger(const MergerLaunch& L, cudaStream_t stream);
 
