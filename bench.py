@@ -256,6 +256,7 @@ def main():
     d_win = torch.empty(total, dtype=torch.uint8, device=dev)
     d_base = torch.empty(total, dtype=torch.float64, device=dev)            # supplied baseline PSNRs: best HEVC intra mode
     h_psnr_all = torch.empty(total, dtype=torch.float64).pin_memory()      # e2e arm: the PSNRs of all sizes land in one pinned array
+    h_gathered = torch.empty(total * world, dtype=torch.float64).pin_memory() if (rank == 0 and world > 1) else None
     per_w, off = {}, 0
     for w, is_fc in WIDTHS:
         idx, rows, cols = offline.blocks_of_images(N_IMAGES, HEIGHT, WIDTH_IMAGE, w)
@@ -318,9 +319,10 @@ def main():
         psnr_all = h_psnr_all
         wins = psnr_all > base_host                      # = (psnr - baseline > 0), comparing_pnn_ipfcns_hevc_best_mode.py:87
         if world > 1:
-            g_psnr, g_win = offline.gather_statistics(psnr_all.to(dev), wins.to(dev), rank, world)
+            g_psnr, g_win = offline.gather_statistics(psnr_all.to(dev, non_blocking=True), wins.to(dev, non_blocking=True),
+                                                      rank, world)
             if rank == 0:
-                return offline.reduce_statistics(g_psnr.cpu().numpy(), g_win.cpu().numpy())
+                return offline.reduce_statistics_device(g_psnr, g_win, pinned=h_gathered)
             return None
         return offline.reduce_statistics(psnr_all.numpy(), wins.numpy())
 

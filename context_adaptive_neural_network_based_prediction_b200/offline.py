@@ -74,6 +74,29 @@ def gather_statistics(psnrs_local, wins_local, rank, world_size, group=None):
     return stacked[:, :n], stacked[:, n:].to(torch.uint8)
 
 
+def reduce_statistics_device(psnrs, wins, pinned=None):
+    """`reduce_statistics` for the gathered torch tensors of rank 0 while they are still on the GPU: the two scalars are
+    reduced on the device, the per-block PSNRs come back through one copy (into `pinned`, a pinned float64 tensor of the
+    same number of elements, when given)."""
+    import torch
+    flat = psnrs.reshape(-1)
+    mean = flat.mean() if flat.numel() else torch.tensor(float('nan'))
+    won = (wins.reshape(-1) != 0).sum()
+    if pinned is not None:
+        host = pinned[:flat.numel()]
+        host.copy_(flat, non_blocking=True)
+    else:
+        host = flat.cpu()
+    mean_host, won_host = float(mean.item()), int(won.item())          # .item() also orders the copy above
+    if psnrs.is_cuda:
+        torch.cuda.current_stream(psnrs.device).synchronize()
+    return {
+        'psnrs_pnn': host.numpy(),
+        'mean_psnr_pnn': mean_host,
+        'frequency_win_pnn': float(won_host) / max(1, flat.numel()),
+    }
+
+
 def reduce_statistics(psnrs, wins):
     """The reference's result keys (comparing_pnn_ipfcns_hevc_best_mode.py:264-322) from the gathered arrays."""
     psnrs = numpy.asarray(psnrs, dtype=numpy.float64).ravel()

@@ -72,3 +72,16 @@ def test_reduce_statistics_matches_reference_formula():
     psnrs, freq = epilogue.performance_vs_baseline(targets, preds, base)
     stats = offline.reduce_statistics(psnrs, (psnrs - base > 0.).astype(numpy.uint8))
     assert stats['frequency_win_pnn'] == freq and abs(stats['mean_psnr_pnn'] - psnrs.mean()) < 1e-12
+
+
+def test_reduce_statistics_device_matches_numpy():
+    """The torch (device-side) reduction used by rank 0 in the multi-rank bench gives the reference's keys and values."""
+    import torch
+    rng = numpy.random.default_rng(3)
+    psnrs = torch.from_numpy(rng.uniform(5., 45., (3, 777)))
+    wins = torch.from_numpy((rng.uniform(size=(3, 777)) > 0.6).astype(numpy.uint8))
+    a = offline.reduce_statistics_device(psnrs, wins)
+    b = offline.reduce_statistics(psnrs.numpy(), wins.numpy())
+    assert abs(a['mean_psnr_pnn'] - b['mean_psnr_pnn']) < 1e-12
+    assert a['frequency_win_pnn'] == b['frequency_win_pnn']
+    numpy.testing.assert_array_equal(a['psnrs_pnn'], b['psnrs_pnn'])
