@@ -482,11 +482,9 @@ struct pnn_handle {
     int32_t* d_hm_staged_mapped = nullptr;   // device alias of hm_staged
     volatile uint64_t* hm_ll = nullptr;      // pinned + mapped {value, seq} pairs written by the fused FC kernel
     uint2* d_hm_ll_mapped = nullptr;
-    volatile int* hm_flag = nullptr;         // pinned + mapped completion flag (unused by the current fused kernel)
-    int* d_hm_flag_mapped = nullptr;
     DevBuf d_splitk;                         // split-K partial sums of the in-loop conv calls
-    DevBuf d_fc_counters, d_fc_xchg, d_fc_stamps;
-    unsigned long long fc_seq = 0, fc_done_total = 0;
+    DevBuf d_fc_xchg, d_fc_stamps;
+    unsigned long long fc_seq = 0;
     bool hm_fused_fc = true;
     bool hm_split_k = true;
     DevBuf d_hm_staged;
@@ -815,12 +813,7 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
         CUDA_TRY(cudaEventCreate(&h->ev1));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t), cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_staged_mapped, h->hm_staged, 0));
-        CUDA_TRY(cudaHostAlloc((void**)&h->hm_flag, 64, cudaHostAllocMapped));
-        *h->hm_flag = 0;
-        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_flag_mapped, (void*)h->hm_flag, 0));
         h->d_splitk.reserve((size_t)64 << 20);
-        h->d_fc_counters.reserve(2 * sizeof(unsigned long long));
-        CUDA_TRY(cudaMemset(h->d_fc_counters.p, 0, 2 * sizeof(unsigned long long)));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_out, 64 * 64 * sizeof(int32_t), cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_mapped, h->hm_out, 0));
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_out_raw, 64 * 64 * sizeof(float), cudaHostAllocMapped));
@@ -898,7 +891,6 @@ void pnn_destroy(pnn_handle* h) {
     if (h->hm_staged) cudaFreeHost(h->hm_staged);
     if (h->hm_out) cudaFreeHost(h->hm_out);
     if (h->hm_out_raw) cudaFreeHost(h->hm_out_raw);
-    if (h->hm_flag) cudaFreeHost((void*)h->hm_flag);
     if (h->hm_ll) cudaFreeHost((void*)h->hm_ll);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
