@@ -404,7 +404,7 @@ def main():
             'unit': 'TFLOP/s', 'frac': achieved / peak,
             # DRAM read + write bytes of one launch from the committed `ncu --set full` capture (profiles/): FC-4 hidden layer,
             # M = 386377 rows, N = K = 1200; its algorithmic bytes (A hi+lo read once + hi/lo output) are 3.709e9
-            'traffic': 3.677e9, 'traffic_launch': 'gemm_tc_kernel M=386377 N=1200 K=1200 (profiles/r1_gemm_tc_full_summary.txt)',
+            'traffic': 3.726e9, 'traffic_launch': 'gemm_tc_kernel M=386377 N=1200 K=1200 (profiles/r1_gemm_tc_full_summary.txt)',
             'traffic_algorithmic_bytes': 3.709e9,
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks
                            else 'fallback 1.59 PFLOP/s (B200_PROFILING.md)',
