@@ -101,6 +101,10 @@ struct Step {
     int IH = 0, IW = 0, OH = 0, OW = 0, C = 0, k = 0, stride = 0, pad = 0, KP = 0;
     float bias_scalar = 0.f;
     std::shared_ptr<ConvFirstWeights> conv_first;   // host copy: travels as a kernel parameter
+    // in-loop (batch-1) scheduling: independent steps (the two branches, the phases of a transposed convolution) carry
+    // different lanes and run on different streams of the captured graph; a `join` step first waits for every lane
+    int lane = 0;
+    bool join = false;
 };
 
 struct Net {
@@ -315,6 +319,7 @@ void build_conv(Net& net, const FlatFile& ff) {
             net.param_count += (int64_t)wt.size() + bs.size();
             Step st;
             st.in0 = cur;
+            st.lane = br;                                       // the two branches are independent
             if (i == 0) {
                 if (pad_x != pad_y) throw std::runtime_error("unexpected asymmetric padding");
                 // first convolution (one input channel): direct FFMA kernel, weights [k*k][C] as stored
@@ -366,6 +371,7 @@ void build_conv(Net& net, const FlatFile& ff) {
         }
         Step st;
         st.kind = STEP_MERGER;
+        st.join = true;
         st.in0 = branch_out[0];
         st.in1 = branch_out[1];
         st.out = add_buf(net, (int64_t)16 * C);
@@ -395,6 +401,7 @@ void build_conv(Net& net, const FlatFile& ff) {
             const int NP = (k * k + 15) / 16 * 16;
             Step gm;
             gm.kind = STEP_GEMM;
+            gm.join = true;
             gm.in0 = cur;
             gm.out = add_buf(net, (int64_t)h * w * NP);
             gm.g = pixel_gemm_geom(h, w, c, NP, 0);
@@ -422,6 +429,8 @@ void build_conv(Net& net, const FlatFile& ff) {
                     st.kind = STEP_GEMM;
                     st.in0 = cur;
                     st.out = out_buf;
+                    st.lane = py * s + px;                      // the phases write disjoint pixels of the same map
+                    st.join = st.lane == 0;
                     GemmGeom& g = st.g;
                     g.P = h * w; g.OW = w; g.Cin = c; g.TH = th; g.TW = tw; g.IH = h; g.IW = w;
                     g.sy_o = 1; g.sy_t = -1; g.cy = (py + pad - ky0) / s;
@@ -487,6 +496,8 @@ struct pnn_handle {
     unsigned long long fc_seq = 0;
     bool hm_fused_fc = true;
     bool hm_split_k = true;
+    cudaStream_t lane_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (= the calling stream)
+    cudaEvent_t lane_fork = nullptr, lane_done[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf d_hm_staged;
     int hm_width = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -585,9 +596,38 @@ Act act_of(Net& net, int buf) {
 }
 
 // Runs every layer of `net` on `n` samples whose contexts are already in the input buffers.
-void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream_t stream, bool allow_split_k = false) {
+void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream_t main_stream, bool allow_split_k = false) {
     const bool split = h->precision == PNN_PRECISION_BF16X3;
+    // In-loop calls (one sample): the kernels are far too small to fill the GPU, so independent steps run concurrently on
+    // lane streams (fork / join with events; inside a stream capture they become parallel branches of the graph).
+    static const bool lanes_enabled = !(getenv("PNN_HM_LANES") && atoi(getenv("PNN_HM_LANES")) == 0);
+    const bool lanes = allow_split_k && lanes_enabled && !h->profiling;
+    bool lane_active[4] = {false, false, false, false};
+    auto join_lanes = [&]() {
+        for (int l = 1; l < 4; ++l) {
+            if (!lane_active[l]) continue;
+            CUDA_TRY(cudaEventRecord(h->lane_done[l], h->lane_stream[l]));
+            CUDA_TRY(cudaStreamWaitEvent(main_stream, h->lane_done[l], 0));
+            lane_active[l] = false;
+        }
+    };
+    if (lanes) CUDA_TRY(cudaEventRecord(h->lane_fork, main_stream));          // the inputs of every lane are ready here
     for (const Step& st : net.steps) {
+        cudaStream_t stream = main_stream;
+        const int lane = lanes ? st.lane : 0;
+        if (lanes) {
+            if (st.join) {
+                join_lanes();
+                CUDA_TRY(cudaEventRecord(h->lane_fork, main_stream));         // everything before this step
+            }
+            if (lane > 0) {
+                stream = h->lane_stream[lane];
+                if (!lane_active[lane]) {
+                    CUDA_TRY(cudaStreamWaitEvent(stream, h->lane_fork, 0));
+                    lane_active[lane] = true;
+                }
+            }
+        }
         switch (st.kind) {
             case STEP_GEMM: {
                 GemmLaunch L{};
@@ -614,9 +654,10 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                         if (kb_per < 2) kb_per = 2;
                         const int slices = (num_kb + kb_per - 1) / kb_per;
                         const size_t need_bytes = (size_t)slices * L.M * st.g.N * sizeof(float);
-                        if (slices > 1 && need_bytes <= h->d_splitk.bytes) {
+                        const size_t region = h->d_splitk.bytes / 4;            // one region per lane
+                        if (slices > 1 && need_bytes <= region) {
                             L.split_k = slices;
-                            L.partial = (float*)h->d_splitk.p;
+                            L.partial = (float*)((char*)h->d_splitk.p + (size_t)lane * region);
                         }
                     }
                 }
@@ -661,6 +702,7 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
             }
         }
     }
+    if (lanes) join_lanes();
     CUDA_TRY(cudaGetLastError());
 }
 
@@ -811,6 +853,11 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
         }
         CUDA_TRY(cudaEventCreate(&h->ev0));
         CUDA_TRY(cudaEventCreate(&h->ev1));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming));
+        for (int l = 1; l < 4; ++l) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->lane_done[l], cudaEventDisableTiming));
+        }
         CUDA_TRY(cudaHostAlloc((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t), cudaHostAllocMapped));
         CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_staged_mapped, h->hm_staged, 0));
         h->d_splitk.reserve((size_t)64 << 20);
@@ -895,6 +942,11 @@ void pnn_destroy(pnn_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->lane_fork) cudaEventDestroy(h->lane_fork);
+    for (int l = 1; l < 4; ++l) {
+        if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
+        if (h->lane_done[l]) cudaEventDestroy(h->lane_done[l]);
+    }
     if (h->stream_in) cudaStreamDestroy(h->stream_in);
     if (h->stream_out) cudaStreamDestroy(h->stream_out);
     for (auto& set : h->in_set) {
