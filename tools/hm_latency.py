@@ -52,7 +52,7 @@ if cpu:
     # (profiles/r1_config3_hm_substitution_1080p_final.json, QP 32) with every PNN call charged at the CPU stand-in's
     # batch-1 latency instead of libpnn_cuda's.
     calls = {4: 130757, 8: 32288, 16: 7857, 32: 1956, 64: 435}
-    encode_s, pnn_s = 12.59 - 4.96 + 4.12, 4.12   # codec time of the fastest box + PNN time of the final build
+    encode_s, pnn_s = 12.59, 4.96
     cpu_pnn_s = sum(calls[w] * results[w][1] * 1e-6 for w in calls)
     print('projection, 1080p frame at QP 32, %d host threads: PNN calls on the CPU stand-in %.1f s -> encode %.1f s; '
           'measured with libpnn_cuda: PNN %.2f s, encode %.2f s; ratio %.1fx'
