@@ -470,7 +470,7 @@ struct pnn_handle {
     std::map<std::pair<int, int>, std::unique_ptr<Net>> nets;   // (width, is_fc)
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
-    size_t workspace_budget = (size_t)8 << 30;
+    size_t workspace_budget = (size_t)20 << 30;   // per net; PNN_WORKSPACE_GB overrides (20 GB: one chunk for the bench's conv nets, 965 -> 500 launches per 5 steps, -0.9 %)
     // host-API staging
     DevBuf d_images, d_idx, d_rows, d_cols, d_in0, d_in1;
     // image-block host path: copies run on their own streams so that the upload of call k+1 and the read-back of call k
@@ -561,7 +561,9 @@ int64_t choose_capacity(pnn_handle* h, const Net& net, int64_t n) {
     int64_t per = 0;
     for (int64_t e : net.buf_elems) per += e * 6;
     per += (int64_t)net.W * net.W * 9 + 8;
-    int64_t cap = std::max<int64_t>(1, (int64_t)(h->workspace_budget / (size_t)per));
+    static const size_t budget_gb = getenv("PNN_WORKSPACE_GB") ? (size_t)atoi(getenv("PNN_WORKSPACE_GB")) : 0;
+    const size_t budget = budget_gb ? budget_gb << 30 : h->workspace_budget;
+    int64_t cap = std::max<int64_t>(1, (int64_t)(budget / (size_t)per));
     // keep rows (cap * positions) comfortably inside int32
     cap = std::min<int64_t>(cap, (int64_t)1 << 19);
     return std::min(cap, std::max<int64_t>(n, 1));
