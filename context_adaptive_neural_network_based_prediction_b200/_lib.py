@@ -17,6 +17,7 @@ EXPORTS = (
     'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation', 'pnn_win_flags_device', 'pnn_set_profiling',
     'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused', 'pnn_hevc_best_mode', 'pnn_hevc_best_mode_device',
     'pnn_inspect_net_file', 'pnn_predict_image_blocks_async', 'pnn_synchronize',
+    'pnn_set_hm_cache', 'pnn_hm_cache_stats', 'pnn_set_workspace_budget', 'pnn_register_net',
 )
 
 PRECISION_FP32 = 0
@@ -44,6 +45,8 @@ def load():
     lib.pnn_last_error.restype = c.c_char_p
     lib.pnn_load_net.argtypes = [vp, c.c_char_p]
     lib.pnn_load_net.restype = i32
+    lib.pnn_register_net.argtypes = [vp, c.c_char_p]
+    lib.pnn_register_net.restype = i32
     lib.pnn_inspect_net_file.argtypes = [c.c_char_p, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int64),
                                          c.POINTER(c.c_double)]
     lib.pnn_inspect_net_file.restype = i32
@@ -88,6 +91,12 @@ def load():
     lib.pnn_hevc_best_mode.restype = i32
     lib.pnn_hevc_best_mode_device.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.pnn_hevc_best_mode_device.restype = i32
+    lib.pnn_set_hm_cache.argtypes = [vp, i32]
+    lib.pnn_set_hm_cache.restype = i32
+    lib.pnn_hm_cache_stats.argtypes = [vp, c.POINTER(i64), c.POINTER(i64)]
+    lib.pnn_hm_cache_stats.restype = i32
+    lib.pnn_set_workspace_budget.argtypes = [vp, i64]
+    lib.pnn_set_workspace_budget.restype = i32
     lib.pnn_version.argtypes = []
     lib.pnn_version.restype = c.c_char_p
     _lib = lib

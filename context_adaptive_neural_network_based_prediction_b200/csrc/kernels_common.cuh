@@ -45,6 +45,33 @@ __device__ __forceinline__ void act_store(const Act& a, int64_t idx, float v) {
     }
 }
 
+// HM gather (reference extraction_context.cpp:56-205): element e of the flattened (above, left) context of width W from
+// its raw reconstruction pixel and the availability description of pnn_internal.h (GatherHmLaunch):
+//   above columns [0, W)             always copied (extraction_context.cpp:119-127)
+//   above columns W + i*unit_w ...   copied iff above unit i is available (:149-166)
+//   left rows [0, left_rows)         copied; the reference writer only advances on available units (:189-205)
+__device__ __forceinline__ float hm_value_from_raw(int raw, int e, int W, float mean, uint32_t lo, uint32_t hi, int unit_w,
+                                                   int left_rows) {
+    float v = (float)raw - mean;
+    const int na = 3 * W * W;
+    if (e < na) {
+        const int cc = e % (3 * W);
+        if (cc >= W) {
+            const int u = (cc - W) / unit_w;
+            const uint32_t bit = u < 32 ? (lo >> u) & 1u : (hi >> (u - 32)) & 1u;
+            if (!bit) v = 0.f;
+        }
+    } else if ((e - na) / W >= left_rows) {
+        v = 0.f;
+    }
+    return v;
+}
+// the same from the staged buffer (header + pixels); unit width 0 = float bits of an already pre-processed context
+__device__ __forceinline__ float hm_context_value(const int32_t* __restrict__ staged, int W, float mean, int e) {
+    if (staged[2] == 0) return __int_as_float(staged[HM_HEADER_INTS + e]);
+    return hm_value_from_raw(staged[HM_HEADER_INTS + e], e, W, mean, (uint32_t)staged[0], (uint32_t)staged[1], staged[2], staged[3]);
+}
+
 // Fused epilogue of the last layer: raw output, and round(clip(p + mean, 0, 255)).
 //   half-even: numpy.round, reference tools/tools.py:49
 //   half-away: std::round, reference TComPrediction.cpp(substitution):632

@@ -1,6 +1,5 @@
 // HBM / latency-bound kernels of the PNN path: fused context gathers, the direct first convolution, channel-wise
-// merger, col2im of the last transposed convolution with the fused epilogue, PSNR / win flags, and the batch-1
-// fully-connected kernels of the in-loop path.
+// merger, col2im of the last transposed convolution with the fused epilogue, PSNR / win flags.
 #include "kernels_common.cuh"
 
 #include <cstdlib>
@@ -66,24 +65,6 @@ int launch_gather_image(const GatherLaunch& L, cudaStream_t stream) {
 //   left rows [0, left_rows_valid)   copied; the reference writer only advances on available units
 //                                    (:189-205), so the copied rows are the first n_avail*unit_h ones.
 // ---------------------------------------------------------------------------------------------
-// value of element e of the flattened (above, left) context of width W, staged as described in pnn_internal.h
-__device__ __forceinline__ float hm_context_value(const int32_t* __restrict__ staged, int W, float mean, int e) {
-    const int na = 3 * W * W;
-    if (staged[2] == 0) return __int_as_float(staged[HM_HEADER_INTS + e]);   // float mode: context already pre-processed
-    float v = (float)staged[HM_HEADER_INTS + e] - mean;
-    if (e < na) {
-        const int cc = e % (3 * W);
-        if (cc >= W) {
-            const int u = (cc - W) / staged[2];
-            const uint32_t bit = u < 32 ? ((uint32_t)staged[0] >> u) & 1u : ((uint32_t)staged[1] >> (u - 32)) & 1u;
-            if (!bit) v = 0.f;
-        }
-    } else if ((e - na) / W >= staged[3]) {
-        v = 0.f;
-    }
-    return v;
-}
-
 template <bool SPLIT>
 __global__ void gather_hm_kernel(GatherHmLaunch L) {
     const int W = L.W;
@@ -104,242 +85,33 @@ int launch_gather_hm(const GatherHmLaunch& L, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Batch-1 fully-connected layer for the in-loop calls (reference TComPrediction.cpp(substitution):566-584
-// runs the FC graphs with a batch of one).  Weight streaming: CTA = 8 output columns x 128 slices of K (150 CTAs for
-// the 1200 hidden units: every SM pulls its share of the K*N*4 bytes, which is what the layer costs -- with 75 CTAs of
-// 16 columns a hidden layer took 3.5 us, the per-SM limit on outstanding loads, not L2 bandwidth).  Every thread
-// requests its <= 10 float4 weights before using the first one; the 128 partial sums of a column are added in a fixed
-// order (four runs of 32 slices, then ((s0 + s1) + s2) + s3): the result does not depend on the launch configuration of
-// anything else, so encoder and decoder reconstructions match bit for bit.  gemv_fp32_kernel (one launch per layer) and
-// fc_chain_kernel (one launch per net) share this function and give identical bits.
+// Weight tiles of the tcgen05 GEMM (layout in pnn_internal.h): one CTA per tile (nt, kb); element (row r = output column,
+// kk = k within the 64-block) goes to byte r*128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7)*2 of the hi plane, the lo
+// plane follows at + bn*128.  Rows / k beyond N / K are zero.
 // ---------------------------------------------------------------------------------------------
-constexpr int GV_KPER_MAX = 10;      // ceil(1280 / 128)
-
-__device__ __forceinline__ void gemv_cols8(const float* __restrict__ wbase, const float* __restrict__ bias, int K, int N, int n0,
-                                           const float* xs, float (*red)[9], float* y_out, bool leaky) {
-    const int cq = threadIdx.x & 1, ks = threadIdx.x >> 1;
-    const int kper = (K + 127) >> 7;
-    const int k0 = ks * kper;
-    int k1 = k0 + kper;
-    if (k1 > K) k1 = K;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    // Unconditional loads (row index clamped) and unconditional FMAs (x = 0 beyond the slice): with predicated loads the
-    // compiler glued every load to its own FMAs, i.e. ten dependent L2 round trips instead of one.
-    // The loads are volatile asm statements (kept in program order) so that all ten are in flight before the first FMA.
-    float4 wv[GV_KPER_MAX];
-    float xv[GV_KPER_MAX];
-#pragma unroll
-    for (int j = 0; j < GV_KPER_MAX; ++j) {
-        const int k = min(k0 + j, K - 1);
-        const float* p = wbase + (int64_t)k * N + n0 + cq * 4;
-        asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wv[j].x), "=f"(wv[j].y), "=f"(wv[j].z), "=f"(wv[j].w) : "l"(p));
-    }
-    // ptxas would still sink each load next to its FMAs to save registers (ten dependent L2 round trips).  Every activation
-    // value is therefore made to depend on all ten loads through `0 * (sum of one component of each)`, which changes no
-    // bit of a finite result and forces the loads to be issued back to back.
-    float pin = 0.f;
-#pragma unroll
-    for (int j = 0; j < GV_KPER_MAX; ++j) pin += wv[j].w;
-#pragma unroll
-    for (int j = 0; j < GV_KPER_MAX; ++j) xv[j] = fmaf(pin, 0.f, k0 + j < k1 ? xs[k0 + j] : 0.f);
-#pragma unroll
-    for (int j = 0; j < GV_KPER_MAX; ++j) {
-        acc[0] = fmaf(xv[j], wv[j].x, acc[0]);
-        acc[1] = fmaf(xv[j], wv[j].y, acc[1]);
-        acc[2] = fmaf(xv[j], wv[j].z, acc[2]);
-        acc[3] = fmaf(xv[j], wv[j].w, acc[3]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) red[ks][cq * 4 + j] = acc[j];
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int col = threadIdx.x & 7, part = threadIdx.x >> 3;
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s += red[part * 32 + j][col];           // fixed order inside a run of 32 slices
-        const float s0 = __shfl_sync(0xffffffffu, s, col), s1 = __shfl_sync(0xffffffffu, s, col + 8);
-        const float s2 = __shfl_sync(0xffffffffu, s, col + 16), s3 = __shfl_sync(0xffffffffu, s, col + 24);
-        if (threadIdx.x < 8) {
-            float v = ((s0 + s1) + s2) + s3 + bias[n0 + col];
-            if (leaky) v = leaky_relu(v);
-            y_out[col] = v;
-        }
+__global__ void __launch_bounds__(256) make_tc_tiles_kernel(const float* __restrict__ w, int K, int N, uint8_t* __restrict__ tiles) {
+    const int num_kb = (K + TC_BK - 1) / TC_BK;
+    const int nt = blockIdx.x / num_kb, kb = blockIdx.x - nt * num_kb;
+    int rem = N - nt * TC_BN;
+    if (rem > TC_BN) rem = TC_BN;
+    const int bn = (rem + 15) / 16 * 16;
+    // every tile before the last N tile is TC_BN rows high
+    uint8_t* hi = tiles + (size_t)nt * num_kb * 2 * TC_BN * 128 + (size_t)kb * 2 * bn * 128;
+    uint8_t* lo = hi + (size_t)bn * 128;
+    for (int idx = threadIdx.x; idx < bn * TC_BK; idx += 256) {
+        const int kk = idx / bn, r = idx - kk * bn;          // r fastest: coalesced reads of w[k][n]
+        const int n = nt * TC_BN + r, k = kb * TC_BK + kk;
+        const float v = (n < N && k < K) ? w[(size_t)k * N + n] : 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        const size_t o = (size_t)r * 128 + (size_t)(((kk >> 3) ^ (r & 7)) << 4) + (size_t)(kk & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(hi + o) = h;
+        *reinterpret_cast<__nv_bfloat16*>(lo + o) = l;
     }
 }
 
-__global__ void __launch_bounds__(256) gemv_fp32_kernel(GemvLaunch L) {
-    // CTA = 8 output columns; N % 8 == 0, K <= 1280
-    __shared__ float xs[1280];
-    __shared__ float red[128][9];
-    for (int k = threadIdx.x; k < L.K; k += 256) xs[k] = L.first ? hm_context_value(L.staged, L.W, L.mean, k) : L.x[k];
-    __syncthreads();
-    gemv_cols8(L.w, L.bias, L.K, L.N, blockIdx.x * 8, xs, red, L.y + blockIdx.x * 8, L.leaky != 0);
-}
-
-// Last FC layer (N = W*W <= 64 outputs): one warp per output, weights transposed to [N][K] on the host so
-// that a warp streams contiguous rows with 16-byte loads; lane partials are combined by a fixed shuffle tree.
-__global__ void __launch_bounds__(128) gemv_last_kernel(GemvLaunch L) {
-    __shared__ __align__(16) float xs[1280];
-    for (int k = threadIdx.x; k < L.K; k += 128) xs[k] = L.x[k];
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 4 + warp;
-    if (n >= L.N) return;
-    const float4* w = (const float4*)(L.w + (int64_t)n * L.K);
-    const float4* x4 = (const float4*)xs;
-    float acc = 0.f;
-    for (int i = lane; i < (L.K >> 2); i += 32) {                  // K % 4 == 0
-        const float4 wv = __ldg(w + i), xv = x4[i];
-        acc = fmaf(xv.x, wv.x, acc);
-        acc = fmaf(xv.y, wv.y, acc);
-        acc = fmaf(xv.z, wv.z, acc);
-        acc = fmaf(xv.w, wv.w, acc);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-        float s = acc + L.bias[n];
-        if (L.leaky) s = leaky_relu(s);
-        final_store(L.fin, n, s);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Fused batch-1 FC net (see FcChainLaunch in pnn_internal.h).  Same arithmetic and reduction order as the
-// gemv_fp32_kernel / gemv_last_kernel pair (the two paths give identical bits).
-// ---------------------------------------------------------------------------------------------
-// Layer-to-layer exchange of the fused kernel without a grid barrier, and its completion signal, in the style of a
-// low-latency collective: every value travels as an 8-byte {bits, tag} pair written with ONE store (8-byte accesses are
-// single-copy atomic), the consumer polls the pair until the tag is the one of this call and layer.  No fence, no atomic
-// counter, no second round trip for the data: one store and one load round trip per layer.
-__device__ __forceinline__ void ll_store(uint2* p, float value, unsigned tag) {
-    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(tag) : "memory");
-}
-__device__ __forceinline__ void ll_store_sys(uint2* p, unsigned bits, unsigned tag) {
-    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(bits), "r"(tag) : "memory");
-}
-// xs[k] <- value of pair k, k = threadIdx.x + 256 j (K <= 1280: at most 5 pairs per thread, polled together)
-__device__ __forceinline__ void ll_collect(const uint2* pairs, int K, unsigned tag, float* xs) {
-    uint2 v[5];
-    bool ready;
-    do {
-        ready = true;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int k = threadIdx.x + 256 * j;
-            if (k < K) {
-                asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[j].x), "=r"(v[j].y) : "l"(pairs + k) : "memory");
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            if (threadIdx.x + 256 * j < K && v[j].y != tag) ready = false;
-        }
-    } while (!ready);
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const int k = threadIdx.x + 256 * j;
-        if (k < K) xs[k] = __uint_as_float(v[j].x);
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) fc_chain_kernel(const __grid_constant__ FcChainLaunch L) {
-    __shared__ __align__(16) float xs[1280];
-    __shared__ float red[128][9];
-    __shared__ float y8[8];
-    auto stamp = [&](int i) {
-        if (L.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            L.stamps[i] = t;
-        }
-    };
-    stamp(0);
-    const unsigned tag0 = (unsigned)L.seq * 4u;                 // tags are unique per call and layer
-    for (int k = threadIdx.x; k < L.K[0]; k += 256) xs[k] = L.ctx[k];      // constant bank (kernel parameters)
-    __syncthreads();
-    for (int layer = 0; layer < 3; ++layer) {
-        gemv_cols8(L.w[layer], L.bias[layer], L.K[layer], L.N[layer], blockIdx.x * 8, xs, red, y8, true);
-        __syncthreads();
-        stamp(1 + 2 * layer);
-        const unsigned tag = tag0 + (unsigned)layer + 1u;
-        if (threadIdx.x < 8) ll_store(L.xchg + layer * 1280 + blockIdx.x * 8 + threadIdx.x, y8[threadIdx.x], tag);
-        if (layer == 2 && blockIdx.x * 8 >= L.N[3]) return;     // only the CTAs that own outputs run the last layer
-        ll_collect(L.xchg + layer * 1280, L.N[layer], tag, xs);
-        stamp(2 + 2 * layer);
-    }
-    // last layer: one warp per output (8 per CTA), weights [N][K]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 8 + warp;
-    if (blockIdx.x * 8 < L.N[3]) {
-        if (n < L.N[3]) {
-            const float4* w = (const float4*)(L.w[3] + (int64_t)n * L.K[3]);
-            const float4* x4 = (const float4*)xs;
-            float acc = 0.f;
-            const int n4 = L.K[3] >> 2;                        // <= 320 float4 per row: 10 per lane, all requested up front
-            float4 wv[10];
-#pragma unroll
-            for (int j = 0; j < 10; ++j) wv[j] = lane + 32 * j < n4 ? __ldg(w + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                if (lane + 32 * j < n4) {
-                    const float4 xv = x4[lane + 32 * j];
-                    acc = fmaf(xv.x, wv[j].x, acc);
-                    acc = fmaf(xv.y, wv[j].y, acc);
-                    acc = fmaf(xv.z, wv[j].z, acc);
-                    acc = fmaf(xv.w, wv[j].w, acc);
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                // the result goes to mapped host memory as {raw bits, seq} and {rounded int, seq} pairs the host polls
-                const float p = acc + L.bias[3][n];
-                const float v = fminf(fmaxf(p + L.fin.mean, 0.f), 255.f);
-                const float r = L.fin.round_mode == 0 ? rintf(v) : roundf(v);
-                ll_store_sys(L.out_ll + n, __float_as_uint(p), (unsigned)L.seq);
-                ll_store_sys(L.out_ll + 64 + n, (unsigned)(int)r, (unsigned)L.seq);
-            }
-        }
-    }
-    stamp(7);
-}
-
-// latency floor of the call pattern (tuning aid, PNN_FC_CHAIN_EMPTY=1): one thread publishes the completion flag
-__global__ void fc_chain_empty_kernel(uint2* out_ll, int n_out, unsigned seq) {
-    if ((int)threadIdx.x < n_out) {
-        ll_store_sys(out_ll + threadIdx.x, 0u, seq);
-        ll_store_sys(out_ll + 64 + threadIdx.x, 0u, seq);
-    }
-}
-
-int launch_fc_chain(const FcChainLaunch& L, cudaStream_t stream) {
-    static const int empty = getenv("PNN_FC_CHAIN_EMPTY") ? atoi(getenv("PNN_FC_CHAIN_EMPTY")) : 0;
-    if (empty) {
-        fc_chain_empty_kernel<<<1, 64, 0, stream>>>(L.out_ll, L.N[3], (unsigned)L.seq);
-        return 1;
-    }
-    // 75 CTAs of 256 threads are always co-resident on the 148 SMs of an otherwise idle B200 (the HM process issues
-    // one synchronous call at a time); a plain launch is several microseconds cheaper than a cooperative one
-    static int coop = -1;
-    if (coop < 0) {
-        const char* e = getenv("PNN_FC_CHAIN_COOPERATIVE");
-        coop = e && atoi(e) != 0;
-    }
-    if (coop) {
-        FcChainLaunch copy = L;
-        void* args[] = {(void*)&copy};
-        cudaLaunchCooperativeKernel((const void*)fc_chain_kernel, dim3(FC_CHAIN_CTAS), dim3(256), args, 0, stream);
-    } else {
-        fc_chain_kernel<<<FC_CHAIN_CTAS, 256, 0, stream>>>(L);
-    }
-    return 1;
-}
-
-int launch_gemv(const GemvLaunch& L, cudaStream_t stream) {
-    if (L.last) gemv_last_kernel<<<(L.N + 3) / 4, 128, 0, stream>>>(L);
-    else gemv_fp32_kernel<<<L.N / 8, 256, 0, stream>>>(L);
+int launch_make_tc_tiles(const float* w_kn, int K, int N, uint8_t* tiles, cudaStream_t stream) {
+    make_tc_tiles_kernel<<<tc_num_nt(N) * tc_num_kb(K), 256, 0, stream>>>(w_kn, K, N, tiles);
     return 1;
 }
 

@@ -111,6 +111,9 @@ inline size_t tc_tile_offset(int N, int K, int nt, int kb) {
 }
 inline size_t tc_total_bytes(int N, int K) { return tc_tile_offset(N, K, tc_num_nt(N), 0); }
 
+// [K][N] fp32 weights (device) -> the tile image described above (device); kernels_small.cu
+int launch_make_tc_tiles(const float* w_kn, int K, int N, uint8_t* tiles, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------------
 // Kernel launchers (implemented in the .cu files).  All asynchronous on `stream`.
 // Each returns the number of kernels it launched.
@@ -190,45 +193,65 @@ struct GatherHmLaunch {
 };
 int launch_gather_hm(const GatherHmLaunch& L, cudaStream_t stream);
 
-// Batch-1 fully-connected layer (in-loop path): y = act(x W + b) as a weight-streaming fp32 GEMV with a
-// fixed reduction order; the first layer reads the staged HM context (gather fused), the last one runs the
-// output epilogue.
-struct GemvLaunch {
-    const float* w;          // [K][N] fp32 ([N][K] for the last layer)
-    const float* bias;
-    const float* x;          // [K] (unused by the first layer)
-    float* y;                // [N] (unused by the last layer)
-    int K, N, leaky;
-    int first, last;
-    const int32_t* staged;   // first layer: header + pixels (see GatherHmLaunch)
-    int W;
+// ---------------------------------------------------------------------------------------------
+// In-loop (batch-1) fully-connected nets, widths 4 and 8 (kernel_fc_inloop.cu).  The 1200 hidden units are cut over
+// FCI_NCTA CTAs (the first FCI_NCTA_WIDE own 9 columns, the others 8); every CTA has a packed image of its weights:
+//   L0 [K0][cols] | L1 [1200][cols] | L2 [1200][cols] | L3 [1200] (CTA o < N3 owns output o) | bias [3][cols] + [1]
+// at a fixed stride of fci_image_floats(K0) floats.
+// ---------------------------------------------------------------------------------------------
+constexpr int FCI_NCTA = 148;
+constexpr int FCI_NCTA_WIDE = 16;        // 16 * 9 + 132 * 8 = 1200
+constexpr int FCI_HID = 1200;
+constexpr int FCI_COLS_MAX = 9;
+constexpr int FCI_CTX_MAX = 320;         // 5 * 8 * 8
+constexpr int FCI_REQ_PAIRS = 352;       // header pair + up to 320 payload pairs, padded to a multiple of 256 bytes
+constexpr int FCI_COPIES = 8;            // identical copies of everything 148 CTAs poll at once (spreads the L2 slices)
+inline int fci_image_floats(int K0) { return (K0 + 2 * FCI_HID) * FCI_COLS_MAX + FCI_HID + 32; }
+std::vector<float> fci_build_images(const float* w0, const float* w1, const float* w2, const float* w3, const float* b0,
+                                    const float* b1, const float* b2, const float* b3, int K0, int N3);
+
+// Request header (payload of pair 0):
+constexpr unsigned FCI_CMD_NET = 1u;     // bit 0: 0 = the width-4 net, 1 = the width-8 net
+constexpr unsigned FCI_CMD_FLOAT = 2u;   // payloads are the float bits of a pre-processed context, one per pair; otherwise
+                                         // 10-bit codes, three per pair: 0..255 = reconstruction pixel (the kernel subtracts
+                                         // the mean), 0x100 = masked / unavailable (-> 0)
+constexpr unsigned FCI_CMD_QUIT = 4u;    // the kernel exits
+
+struct FciNet {
+    const float* images;    // [FCI_NCTA][stride]
+    int K0, N3, W, present, stride;
+};
+// Persistent kernel: one CTA per SM for the life of the kernel, the images of both nets in shared memory.  A request is a
+// header pair + payload pairs {payload, seq} written by the host into mapped pinned memory.  CTA 0 polls the first 32
+// pairs (one 256-byte read per PCIe round trip; a whole 4x4 context fits), decodes the context and relays it to the
+// other CTAs through device memory; layers hand their 1200 activations over as {bits, tag} pairs; the CTAs that own an
+// output write {raw bits, seq} and {rounded int, seq} into mapped pinned memory, which the host polls.
+struct FciPersist {
+    FciNet net[2];
+    const uint2* req;       // mapped host memory [FCI_REQ_PAIRS]
+    uint2* relay;           // device memory      [FCI_COPIES][FCI_REQ_PAIRS]
+    uint2* xchg;            // device memory      [3][FCI_COPIES][FCI_HID]
+    uint2* out_ll;          // mapped host memory [64] raw + [64] rounded
+    float mean;
+    int round_mode;
+    unsigned seq0;          // sequence number of the first request this launch serves
+    unsigned long long* stamps;   // tuning aid (PNN_FC_STAMPS=1): %globaltimer at 9 points of a call, or NULL
+};
+size_t fci_persist_smem_bytes(const FciPersist& P);
+cudaError_t launch_fci_persist(const FciPersist& P, cudaStream_t stream);
+
+// One layer per launch (CUDA-graph fall-back, same bits): layer 0 reads the staged context (see GatherHmLaunch),
+// layers 1-2 read x[1200], layer 3 (grid = N3) runs the output epilogue.
+struct FciLayerLaunch {
+    const float* images;
+    int K0, N3, W, stride, layer;
+    const int32_t* staged;
+    const float* x;
+    float* y;
     float mean;
     FinalOut fin;
 };
-int launch_gemv(const GemvLaunch& L, cudaStream_t stream);
-
-// Whole batch-1 FC net in ONE cooperative kernel (75 CTAs, grid barriers between the layers): CTA 0 pulls the
-// staged context from mapped pinned host memory, every layer is the weight-streaming GEMV of gemv_fp32_kernel,
-// the last layer writes the prediction into mapped pinned memory and the last CTA to finish publishes
-// `seq` in a mapped flag the host spins on (no copy nodes, no stream synchronise).
-struct FcChainLaunch {
-    const float* w[4];               // [K][N] fp32; w[3] is transposed to [N][K]
-    const float* bias[4];
-    int K[4], N[4];
-    // The pre-processed context (mean-centred, masked; 80 or 320 floats) travels IN the kernel parameters: the launch
-    // packet carries it to the GPU, so no CTA reads host memory over PCIe and the grid barrier that published the staged
-    // copy is gone (4 -> 3 barriers per call).
-    float ctx[320];
-    uint2* xchg;                     // [3 layers][1280] {value bits, tag} pairs (zero-initialised once)
-    FinalOut fin;                    // mean and rounding mode of the output epilogue
-    uint2* out_ll;                   // mapped pinned host memory: [64] {raw bits, seq} then [64] {rounded int, seq}
-    unsigned long long seq;          // 1, 2, 3, ... per call
-    unsigned long long* stamps;      // tuning aid (PNN_FC_STAMPS=1): %globaltimer of CTA 0 at 10 points, or NULL
-    int W;
-    float mean;
-};
-constexpr int FC_CHAIN_CTAS = 150;   // 1200 hidden units / 8 columns per CTA (two CTAs on two of the 148 SMs)
-int launch_fc_chain(const FcChainLaunch& L, cudaStream_t stream);
+int launch_fci_layer(const FciLayerLaunch& L, cudaStream_t stream);
 void small_kernels_init();
 
 // Best HEVC intra mode of every block (35 modes on an unfiltered pattern) -- the baseline of the offline evaluation.

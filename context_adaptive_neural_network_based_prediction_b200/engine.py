@@ -63,6 +63,10 @@ class Engine(object):
     def load_net(self, path):
         self._check(self._lib.pnn_load_net(self._h, path.encode()))
 
+    def register_net(self, path):
+        """Validates the file now, uploads the weights at first use (C ABI pnn_register_net)."""
+        self._check(self._lib.pnn_register_net(self._h, path.encode()))
+
     def set_precision(self, precision):
         """'fp32' (FFMA yard-stick) or 'bf16x3' (tcgen05, default)."""
         code = {'fp32': _lib.PRECISION_FP32, 'bf16x3': _lib.PRECISION_BF16X3}[precision]
@@ -77,8 +81,22 @@ class Engine(object):
         return float(self._lib.pnn_last_hm_device_ms(self._h))
 
     def set_hm_fused(self, enabled):
-        """In-loop FC nets: fused cooperative kernel (default) or the CUDA-graph GEMV chain."""
+        """In-loop nets: persistent shared-memory-resident FC kernel + split-K conv graphs (default) or plain CUDA graphs."""
         self._check(self._lib.pnn_set_hm_fused(self._h, int(bool(enabled))))
+
+    def set_hm_cache(self, enabled):
+        """Memo of in-loop results keyed by the exact context (C ABI pnn_set_hm_cache); off by default."""
+        self._check(self._lib.pnn_set_hm_cache(self._h, int(bool(enabled))))
+
+    @property
+    def hm_cache_stats(self):
+        hits, misses = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.pnn_hm_cache_stats(self._h, ctypes.byref(hits), ctypes.byref(misses)))
+        return hits.value, misses.value
+
+    def set_workspace_budget(self, bytes_per_net):
+        """Activation workspace one net may use; batched calls are cut into chunks that fit (results do not depend on it)."""
+        self._check(self._lib.pnn_set_workspace_budget(self._h, int(bytes_per_net)))
 
     def set_profiling(self, enabled):
         self._check(self._lib.pnn_set_profiling(self._h, int(bool(enabled))))

@@ -44,5 +44,13 @@ for V in $VARIANTS; do
   g++ -o "$OUT/TAppEncoderStatic_$V" $OBJ/enc_*.o $OBJ/lib_*.o $LINK
   g++ -o "$OUT/TAppDecoderStatic_$V" $OBJ/dec_*.o $OBJ/lib_*.o $LINK
   echo "built $OUT/TAppEncoderStatic_$V and $OUT/TAppDecoderStatic_$V"
+  # Baseline leg: the SAME objects linked against oracle/_ref/libpnn_ref.so, the libtorch-CPU
+  # stand-in for the reference's TensorFlow-CPU build (same C ABI, same link seam) -> *_cpu executables
+  if [ "$V" != "regular" ] && [ -f "$ROOT/oracle/_ref/libpnn_ref.so" ]; then
+    LINKCPU="-L$ROOT/oracle/_ref -lpnn_ref -Wl,-rpath,\$ORIGIN/../../oracle/_ref -lpthread -ldl"
+    g++ -o "$OUT/TAppEncoderStatic_${V}_cpu" $OBJ/enc_*.o $OBJ/lib_*.o $LINKCPU
+    g++ -o "$OUT/TAppDecoderStatic_${V}_cpu" $OBJ/dec_*.o $OBJ/lib_*.o $LINKCPU
+    echo "built $OUT/TAppEncoderStatic_${V}_cpu and $OUT/TAppDecoderStatic_${V}_cpu (CPU baseline backend)"
+  fi
 done
 cp "$REF/hevc/configuration/intra_main_rext.cfg" "$OUT/intra_main_rext.cfg"

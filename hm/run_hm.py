@@ -18,6 +18,11 @@ ap.add_argument('--height', type=int, default=1080)
 ap.add_argument('--qps', default='22,27,32,37')
 ap.add_argument('--variant', default='substitution')
 ap.add_argument('--seed', type=int, default=0)
+ap.add_argument('--backend', default='cuda', choices=('cuda', 'cpu', 'null'),
+                help='cuda: libpnn_cuda (the product); cpu: the *_cpu executables = same codec objects linked against '
+                     'oracle/_ref/libpnn_ref.so (libtorch-CPU stand-in for the TensorFlow-CPU build, the baseline leg); '
+                     'null: the same with PNN_REF_NULL=1 (predictions are zeros at once: the codec\'s own time)')
+ap.add_argument('--keep', default='', help='directory that receives the bitstreams and reconstructions (for rd_compare)')
 ap.add_argument('--image', default='', help='.npy uint8 luminance image instead of the synthetic frame')
 ap.add_argument('--trained-small-nets', action='store_true',
                 help='widths 4 and 8 use the two pretrained checkpoints the reference ships (CONV-4, CONV-8, tests/golden/)')
@@ -27,10 +32,16 @@ ap.add_argument('--frozen-graphs', action='store_true',
 args = ap.parse_args()
 
 build = os.path.join(ROOT, 'hm', '_build')
-enc = os.path.join(build, 'TAppEncoderStatic_' + args.variant)
-dec = os.path.join(build, 'TAppDecoderStatic_' + args.variant)
+suffix = '' if args.backend == 'cuda' or args.variant == 'regular' else '_cpu'
+enc = os.path.join(build, 'TAppEncoderStatic_' + args.variant + suffix)
+dec = os.path.join(build, 'TAppDecoderStatic_' + args.variant + suffix)
+if args.backend == 'null':
+    os.environ['PNN_REF_NULL'] = '1'
 cfg = os.path.join(build, 'intra_main_rext.cfg')
 tmp = tempfile.mkdtemp(prefix='pnn_hm_')
+if args.keep:
+    os.makedirs(args.keep, exist_ok=True)
+    tmp = args.keep
 # weights: FC-4, FC-8, CONV-16, CONV-32, CONV-64 (hevc/hm_common/paths_to_graphs_output/pair.txt format)
 lines = []
 for w, is_fc in ((4, True), (8, True), (16, False), (32, False), (64, False)):
@@ -84,6 +95,7 @@ for qp in [int(q) for q in args.qps.split(',')]:
     same = os.path.exists(rec_e) and os.path.exists(rec_d) and open(rec_e, 'rb').read() == open(rec_d, 'rb').read()
     print(json.dumps({
         'config': 'configs[3]: HM-16.15 %s, first-frame intra, %s %dx%d 4:0:0, intra_main_rext.cfg' % (args.variant, os.path.basename(args.image) if args.image else 'synthetic', args.width, args.height),
+        'backend': args.backend, 'host_cores': os.cpu_count(),
         'trained_small_nets': args.trained_small_nets, 'qp': qp, 'encoder_wall_s': t_enc, 'encoder_total_time_s': float(enc_total[0]) if enc_total else None,
         'decoder_wall_s': t_dec, 'decoder_total_time_s': float(dec_total[0]) if dec_total else None,
         'bytes': int(bits[0]) if bits else None, 'y_psnr_kbps': psnr[0] if psnr else None,

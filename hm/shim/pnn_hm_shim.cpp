@@ -29,6 +29,11 @@ void print_stats() {
         seconds += g_seconds[i];
     }
     fprintf(f, "pnn_calls total: %lld calls, %.6f s\n", total, seconds);
+    if (g_handle) {
+        int64_t hits(0), misses(0);
+        pnn_hm_cache_stats(g_handle, &hits, &misses);
+        fprintf(f, "pnn_cache: %lld hits, %lld misses\n", (long long)hits, (long long)misses);
+    }
     if (f != stderr) fclose(f);
     if (g_handle) {
         pnn_destroy(g_handle);
@@ -48,6 +53,10 @@ pnn_handle* handle() {
             fprintf(stderr, "%s\n", pnn_last_error(NULL));
             return NULL;
         }
+        // the codec evaluates the same unit with the same context in its fast pass, its RD pass and the final
+        // reconstruction: answer repeated contexts from the library's memo (PNN_HM_CACHE=0 switches it off)
+        const char* cache = getenv("PNN_HM_CACHE");
+        pnn_set_hm_cache(g_handle, cache ? atoi(cache) : 1);
         atexit(print_stats);
     }
     return g_handle;
@@ -125,7 +134,8 @@ tensorflow::Status load_graph(const tensorflow::string& path_to_graph_output,
     }
     pnn_handle* h(handle());
     if (!h) return tensorflow::Status("libpnn_cuda could not be initialised");
-    if (pnn_load_net(h, path.c_str()) != 0) return tensorflow::Status(pnn_last_error(h));
+    // validated now, uploaded the first time the codec needs this width
+    if (pnn_register_net(h, path.c_str()) != 0) return tensorflow::Status(pnn_last_error(h));
     unique_ptr_session.reset(new tensorflow::Session(static_cast<int>(width), is_fc != 0));
     return tensorflow::Status::OK();
 }

@@ -66,8 +66,18 @@ const char* pnn_last_error(pnn_handle* h);
 int pnn_load_net(pnn_handle* h, const char* path);
 
 /*
+ * Same as pnn_load_net, but only VALIDATES the file now (a PNNW header listing every tensor the net needs with the right
+ * shapes and sizes, or a whole frozen graph) and uploads the weights the first time a call needs this net.  A decoder that
+ * never meets the neural-network mode at some block width never pays for that net (transform blocks are <= 32x32,
+ * hevc/configuration/intra_main_rext.cfg:13, so a decoder never uses the 64x64 net).  pnn_create with a paths file
+ * registers its five nets this way.
+ */
+int pnn_register_net(pnn_handle* h, const char* path);
+
+/*
  * Host-only (needs no GPU): parses a weights file exactly as pnn_load_net does and reports what it holds.
- * `checksum` = sum over the tensors in name order of sum_i (i % 7 + 1) * value_i, in double.  Any output may be NULL.
+ * `checksum` = sum over the tensors in name order of sum_i (i % 7 + 1) * value_i, in double.  Any output may be NULL
+ * (without `checksum` only the header of a PNNW file is read).
  * Returns 0, or -1 with the message in pnn_last_error(NULL).
  */
 int pnn_inspect_net_file(const char* path, int* width_target, int* is_fully_connected, int64_t* n_parameters,
@@ -162,10 +172,30 @@ int pnn_predict_image_blocks_device(pnn_handle* h, int width, int is_fully_conne
                                     float* d_out_f32, uint8_t* d_out_u8, double* d_out_psnr, void* cuda_stream);
 
 /*
- * In-loop FC nets (widths 4, 8): 1 (default) = one fused cooperative kernel per call with completion through a
- * mapped flag; 0 = four GEMV kernels replayed as a CUDA graph.  Both give identical bits.
+ * In-loop latency path.  1 (default): the FC nets of widths 4 and 8 are served by ONE persistent kernel whose CTAs keep
+ * the weights of both nets in shared memory for the life of the kernel; a call is a doorbell write into mapped pinned
+ * memory and a poll of the answer, no launch.  The kernel leaves the SMs whenever the handle is asked for anything else
+ * (a convolutional net, the offline path) and comes back behind that work.  Convolutional nets: CUDA graph with split-K.
+ * 0: every net is a CUDA graph of plain launches (FC: one launch per layer).  Both settings give identical bits for the
+ * FC nets (same device functions, same reduction order); if the device cannot hold the persistent kernel (148 co-resident
+ * CTAs) the library falls back to 0 for the FC nets by itself.
  */
 int pnn_set_hm_fused(pnn_handle* h, int enabled);
+
+/*
+ * Memo of in-loop results (off by default; the HM bindings switch it on): the codec evaluates the same prediction unit
+ * with the same context several times (fast pass, rate-distortion pass, final reconstruction:
+ * TEncSearch.cpp(substitution):2331-2393, 1229-1250), and a PNN is a pure function of its context, so a context seen
+ * before is answered from host memory -- bit-identical by construction (the whole context is compared, not a hash).
+ */
+int pnn_set_hm_cache(pnn_handle* h, int enabled);
+int pnn_hm_cache_stats(pnn_handle* h, int64_t* hits, int64_t* misses);
+
+/*
+ * Bytes of activation workspace one net may use (default 20 GB, or PNN_WORKSPACE_GB at pnn_create): batched calls are
+ * cut into chunks that fit.  Results do not depend on it (a block's prediction is independent of its batch).
+ */
+int pnn_set_workspace_budget(pnn_handle* h, int64_t bytes_per_net);
 
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */
 int64_t pnn_launch_count(pnn_handle* h);

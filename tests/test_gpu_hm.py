@@ -176,3 +176,152 @@ def test_hm_split_k_matches_plain_kernels(engine, weights_dir, width):
     finally:
         engine.set_hm_fused(True)
     assert numpy.abs(outs[True] - outs[False]).max() <= 1
+
+
+def _fc_context(width, seed):
+    return numpy.random.default_rng(seed).normal(0., 30., 5 * width * width).astype(numpy.float32)
+
+
+def test_persistent_fc_kernel_serves_calls_without_launches(engine, weights_dir):
+    """The FC nets of widths 4 and 8 live in ONE persistent kernel: after its launch an in-loop call is a doorbell write
+    and a poll, whichever of the two nets it addresses; results equal the layer-per-launch graphs bit for bit and the
+    oracle within the parity bound."""
+    from oracle import nets
+    wts = {}
+    for width in (4, 8):
+        path, wts[width] = helpers.make_net_file(weights_dir, width, True, seed=170 + width, gain=helpers.GAIN[(width, True)])
+        engine.load_net(path)
+    engine.set_hm_fused(True)
+    engine.predict_hm_context(4, _fc_context(4, 0))                     # starts the kernel
+    before = engine.launch_count
+    outs = []
+    for i in range(40):
+        width = 4 if i % 3 else 8
+        outs.append((width, i, engine.predict_hm_context(width, _fc_context(width, i))))
+    launched = engine.launch_count - before
+    try:
+        engine.set_hm_fused(False)
+        for width, i, raw in outs:
+            numpy.testing.assert_array_equal(raw, engine.predict_hm_context(width, _fc_context(width, i)))
+            helpers.check_parity(raw, nets.forward_fc(wts[width], _fc_context(width, i)[None])[0, :, :, 0])
+    finally:
+        engine.set_hm_fused(True)
+    assert launched == 0, 'the persistent kernel was not used (%d launches for 40 calls)' % launched
+
+
+def test_interleaved_fc_and_conv_calls(engine, weights_dir):
+    """The codec alternates one convolutional call with tens of FC calls: the persistent kernel leaves the SMs for the
+    convolutional graph and comes back behind it; every result equals the one of the plain-graph mode."""
+    nets_ = ((4, True), (8, True), (16, False))
+    for width, is_fc in nets_:
+        path, _ = helpers.make_net_file(weights_dir, width, is_fc, seed=180 + width, gain=helpers.GAIN[(width, is_fc)])
+        engine.load_net(path)
+    engine.set_precision('bf16x3')
+    plane = helpers.synthetic_image(80, 96, 3).astype(numpy.int32)
+
+    def run():
+        outs = []
+        for i in range(60):
+            width = (16, 8, 4, 4, 4, 4)[i % 6]
+            units = 2 * width // 4
+            flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+            if i % 4 == 1:
+                flags[:units // 2] = 0
+            engine.set_context(width, plane, 20 + i % 7, 24 + i % 5, flags, int(flags.sum()))
+            outs.append(engine.predict_hm(width).copy())
+        return outs
+    fused = run()
+    again = run()
+    for a, b in zip(fused, again):
+        numpy.testing.assert_array_equal(a, b)
+    # FC results are bit-identical across the two modes (same device functions); the convolutional ones within one level
+    try:
+        engine.set_hm_fused(False)
+        plain = run()
+    finally:
+        engine.set_hm_fused(True)
+    for i, (a, b) in enumerate(zip(fused, plain)):
+        if (16, 8, 4, 4, 4, 4)[i % 6] <= 8:
+            numpy.testing.assert_array_equal(a, b)
+        else:
+            assert numpy.abs(a - b).max() <= 1
+
+
+@pytest.mark.parametrize('width', [4, 16])
+def test_hm_cache_answers_repeated_contexts_identically(engine, weights_dir, width):
+    """pnn_set_hm_cache: a context seen before is answered from host memory with the very same bits; a context that
+    differs in one pixel, or in one availability flag, is computed."""
+    is_fc = width <= 8
+    path, _ = helpers.make_net_file(weights_dir, width, is_fc, seed=190 + width, gain=helpers.GAIN[(width, is_fc)])
+    engine.load_net(path)
+    plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 21).astype(numpy.int32)
+    units = 2 * width // 4
+    flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+
+    def call(p, f):
+        engine.set_context(width, p, width + 3, width + 5, f, int(f.sum()))
+        return engine.predict_hm(width).copy()
+    try:
+        engine.set_hm_cache(False)
+        want = call(plane, flags)
+        plane2 = plane.copy(); plane2[3, width + 6] += 9               # one pixel of the above portion
+        want2 = call(plane2, flags)
+        flags3 = flags.copy(); flags3[-1] = 0                          # last above-right unit unavailable
+        want3 = call(plane, flags3)
+        engine.set_hm_cache(True)
+        h0, m0 = engine.hm_cache_stats
+        got = [call(plane, flags), call(plane, flags), call(plane2, flags), call(plane, flags3), call(plane2, flags)]
+        h1, m1 = engine.hm_cache_stats
+    finally:
+        engine.set_hm_cache(False)
+    assert (h1 - h0, m1 - m0) == (2, 3)
+    for g, w in zip(got, (want, want, want2, want3, want2)):
+        numpy.testing.assert_array_equal(g, w)
+    assert (want != want2).any() and (want != want3).any()
+
+
+def test_wide_fc_net_in_loop_uses_the_batched_kernels(engine, weights_dir):
+    """An FC net of width 16 (an offline comparison net, 1280 inputs, 256 outputs) asked for in-loop does not fit the
+    batch-1 FC kernels (5*W*W <= 320): it must go through the batched kernels with one sample, not overflow them."""
+    from oracle import nets
+    from context_adaptive_neural_network_based_prediction_b200 import Engine
+    eng = Engine()
+    try:
+        path, wts = helpers.make_net_file(weights_dir, 16, True, seed=216, gain=1.6)
+        eng.load_net(path)
+        for seed in range(3):
+            flat = _fc_context(16, seed)
+            raw = eng.predict_hm_context(16, flat)
+            helpers.check_parity(raw, nets.forward_fc(wts, flat[None])[0, :, :, 0])
+            numpy.testing.assert_array_equal(raw, eng.predict_hm_context(16, flat))
+    finally:
+        eng.close()
+
+
+def test_registered_nets_load_at_first_use(weights_dir):
+    """pnn_register_net validates the header at once and uploads at first use; a file that lacks a tensor is refused at
+    registration (as load_graph fails at start-up, integration_prediction_neural_network.cpp:29-54)."""
+    import os
+    from oracle import nets
+    from context_adaptive_neural_network_based_prediction_b200 import Engine, PnnError, weights as W
+    eng = Engine()
+    try:
+        path, wts = helpers.make_net_file(weights_dir, 8, True, seed=230, gain=1.6)
+        eng.register_net(path)
+        before = eng.launch_count
+        flat = _fc_context(8, 1)
+        helpers.check_parity(eng.predict_hm_context(8, flat), nets.forward_fc(wts, flat[None])[0, :, :, 0])
+        assert eng.launch_count > before
+        # the same tensors under the header of a width-4 net: the table no longer matches what the net needs
+        bad = os.path.join(weights_dir, 'broken_fc8.pnnw')
+        data = bytearray(open(path, 'rb').read())
+        data[8:12] = (4).to_bytes(4, 'little')
+        open(bad, 'wb').write(bytes(data))
+        with pytest.raises(PnnError, match='unexpected shape'):
+            eng.register_net(bad)
+        truncated = os.path.join(weights_dir, 'truncated_fc8.pnnw')
+        open(truncated, 'wb').write(open(path, 'rb').read()[:1 << 20])
+        with pytest.raises(PnnError):
+            eng.register_net(truncated)
+    finally:
+        eng.close()

@@ -184,3 +184,114 @@ def test_async_image_blocks_equal_sync(engine, weights_dir):
     for a, b in zip(sync, asyn):
         for key in ('predictions_float32', 'predictions_uint8', 'psnrs'):
             numpy.testing.assert_array_equal(a[key], b[key])
+
+
+@pytest.mark.parametrize('width,is_fc,n_chunks', [(4, True, 3), (32, False, 4)])
+def test_multi_chunk_parity_with_ragged_tail(engine, weights_dir, width, is_fc, n_chunks):
+    """A small workspace budget (C ABI pnn_set_workspace_budget) cuts the call into >= 3 chunks with a ragged tail: the
+    predictions match the oracle and are bit-identical to the single-chunk run (what bench.py does at full size, where
+    FC-4 runs as two chunks)."""
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=91 + width, gain=helpers.GAIN[(width, is_fc)])
+    engine.load_net(path)
+    engine.set_precision('bf16x3')
+    images = _image_set(2, max(96, 4 * width), max(160, 6 * width))
+    rows, cols, idx = _blocks(images, width, 1000 if is_fc else 45)
+    n = len(rows)
+    per_sample = {True: 24 * 1024, False: 1200 * 1024}[is_fc]               # upper bounds of the bytes per sample
+    try:
+        engine.set_workspace_budget(20 << 30)
+        whole = engine.predict_image_blocks(width, is_fc, images, rows, cols, idx)
+        engine.set_workspace_budget(max(1, n // n_chunks - 1) * per_sample)
+        before = engine.launch_count
+        cut = engine.predict_image_blocks(width, is_fc, images, rows, cols, idx)
+        launches_cut = engine.launch_count - before
+        before = engine.launch_count
+        engine.set_workspace_budget(20 << 30)
+        engine.predict_image_blocks(width, is_fc, images, rows, cols, idx)
+        launches_whole = engine.launch_count - before
+    finally:
+        engine.set_workspace_budget(20 << 30)
+    assert launches_cut >= 2 * launches_whole, 'the small budget did not produce several chunks'
+    for key in ('predictions_float32', 'predictions_uint8', 'psnrs'):
+        numpy.testing.assert_array_equal(whole[key], cut[key])
+    pred, u8, psnrs, _ = helpers.oracle_predict_blocks(wts, width, is_fc, images, idx, rows, cols)
+    helpers.check_parity(cut['predictions_float32'], pred, cut['predictions_uint8'], u8)
+
+
+@pytest.mark.parametrize('width,is_fc', [(4, True), (8, True), (16, False), (32, False)])
+def test_parity_on_the_bench_shapes(engine, weights_dir, width, is_fc):
+    """BASELINE.json configs[1] shapes: 320 x 480 images, EVERY grid block of two of them, the bench's nets (no gain)."""
+    path, wts = helpers.make_net_file(weights_dir, width, is_fc, seed=width, bias_std=0., gain=1.)
+    engine.load_net(path)
+    engine.set_precision('bf16x3')
+    images = _image_set(2, 320, 480)
+    rows, cols, idx = _blocks(images, width)
+    assert len(rows) == 2 * (320 // width - 1) * (480 // width - 1)
+    out = engine.predict_image_blocks(width, is_fc, images, rows, cols, idx)
+    pred, u8, psnrs, _ = helpers.oracle_predict_blocks(wts, width, is_fc, images, idx, rows, cols)
+    helpers.check_parity(out['predictions_float32'], pred, out['predictions_uint8'], u8)
+    same = (out['predictions_uint8'] == u8).reshape(len(rows), -1).all(axis=1)
+    numpy.testing.assert_allclose(out['psnrs'][same], psnrs[same], rtol=0, atol=1e-9)
+
+
+def test_conv64_parity_on_64_blocks(engine, weights_dir):
+    """BASELINE.json configs[2] net at a batch that fills several M tiles of every layer."""
+    path, wts = helpers.make_net_file(weights_dir, 64, False, seed=164, gain=helpers.GAIN[(64, False)])
+    engine.load_net(path)
+    engine.set_precision('bf16x3')
+    images = _image_set(2, 4 * 64, 10 * 64)
+    rows, cols, idx = _blocks(images, 64, 64)
+    assert len(rows) >= 48
+    out = engine.predict_image_blocks(64, False, images, rows, cols, idx)
+    pred, u8, psnrs, _ = helpers.oracle_predict_blocks(wts, 64, False, images, idx, rows, cols)
+    assert numpy.abs(pred).max() > 3.
+    helpers.check_parity(out['predictions_float32'], pred, out['predictions_uint8'], u8)
+
+
+def test_create_with_paths_file(weights_dir, tmp_path):
+    """pnn_create with the reference's paths file (`width,is_pair,0,path`): single models below QP 32, pair models from
+    QP 32 on when the file lists them, an error when a width is missing (TComPrediction.cpp(substitution):145-171)."""
+    from context_adaptive_neural_network_based_prediction_b200 import Engine, PnnError
+    from oracle import nets
+    single, pair, wts = {}, {}, {}
+    for width in (4, 8, 16, 32, 64):
+        is_fc = width <= 8
+        single[width], wts[(width, 0)] = helpers.make_net_file(weights_dir, width, is_fc, seed=300 + width, gain=helpers.GAIN[(width, is_fc)])
+        pair[width], wts[(width, 1)] = helpers.make_net_file(weights_dir, width, is_fc, seed=400 + width, gain=helpers.GAIN[(width, is_fc)])
+    only_single = str(tmp_path / 'single.txt')
+    open(only_single, 'w').write(''.join('%d,0,0,%s\n' % (w, single[w]) for w in single))
+    both = str(tmp_path / 'pair.txt')
+    open(both, 'w').write(''.join('%d,0,0,%s\n%d,1,0,%s\n' % (w, single[w], w, pair[w]) for w in single) + '\n')
+    missing = str(tmp_path / 'missing.txt')
+    open(missing, 'w').write(''.join('%d,0,0,%s\n' % (w, single[w]) for w in (4, 8, 16, 64)))
+    rng = numpy.random.default_rng(5)
+    ctx = {w: rng.normal(0., 30., 5 * w * w).astype(numpy.float32) for w in (4, 16)}
+
+    def which(engine, width):
+        """0 if the engine answers with the single model of this width, 1 if with the pair model."""
+        flat = ctx[width]
+        raw = engine.predict_hm_context(width, flat if width <= 8 else flat[:3 * width * width],
+                                        None if width <= 8 else flat[3 * width * width:])
+        errs = []
+        for is_pair in (0, 1):
+            if width <= 8:
+                ref = nets.forward_fc(wts[(width, is_pair)], flat[None])[0, :, :, 0]
+            else:
+                ref = nets.forward_conv(wts[(width, is_pair)], flat[:3 * width * width].reshape(1, width, 3 * width, 1),
+                                        flat[3 * width * width:].reshape(1, 2 * width, width, 1))[0, :, :, 0]
+            errs.append(float(numpy.abs(raw - ref).max()))
+        assert min(errs) <= 1e-2 < max(errs)
+        return int(numpy.argmin(errs))
+
+    for paths_file, qp, expected in ((only_single, 22, 0), (only_single, 37, 0), (both, 31, 0), (both, 32, 1)):
+        eng = Engine(paths_file=paths_file, qp_selection=qp)
+        try:
+            assert which(eng, 4) == expected and which(eng, 16) == expected
+        finally:
+            eng.close()
+    with pytest.raises(PnnError, match='width 32'):
+        Engine(paths_file=missing, qp_selection=22)
+    with pytest.raises(PnnError):
+        Engine(paths_file=str(tmp_path / 'absent.txt'), qp_selection=22)
+    with pytest.raises(PnnError, match='quantization parameter'):
+        Engine(paths_file=only_single, qp_selection=0)

@@ -44,16 +44,8 @@ for width in (4, 8, 16, 32, 64):
         for _ in range(20):
             nets.forward(wts, width, is_fc, args)
         cpu_us = (time.perf_counter() - t0) / 20 * 1e6
-    d = max(float(numpy.median(dev)) * 1e3, 1e-9)
-    print('%3d %10.1f %10.1f %12.1f %12.1f' % (width, wall, d, params[width] * 4 / (d * 1e-6) / 1e9, cpu_us), flush=True)
+    # the persistent FC kernel serves a call without a launch: there are no events to time it with, only the wall clock
+    d = float(numpy.median(dev)) * 1e3
+    print('%3d %10.1f %10s %12.1f %12.1f' % (width, wall, '%.1f' % d if d > 0 else 'n/a (persistent)',
+                                             params[width] * 4 / ((d if d > 0 else wall) * 1e-6) / 1e9, cpu_us), flush=True)
     results[width] = (wall, cpu_us)
-if cpu:
-    # Projection for BASELINE.json configs[3] (the TF-CPU build cannot be run): the measured encode of the final build
-    # (profiles/r1_config3_hm_substitution_1080p_final.json, QP 32) with every PNN call charged at the CPU stand-in's
-    # batch-1 latency instead of libpnn_cuda's.
-    calls = {4: 130757, 8: 32288, 16: 7857, 32: 1956, 64: 435}
-    encode_s, pnn_s = 12.59, 4.96
-    cpu_pnn_s = sum(calls[w] * results[w][1] * 1e-6 for w in calls)
-    print('projection, 1080p frame at QP 32, %d host threads: PNN calls on the CPU stand-in %.1f s -> encode %.1f s; '
-          'measured with libpnn_cuda: PNN %.2f s, encode %.2f s; ratio %.1fx'
-          % (os.cpu_count(), cpu_pnn_s, encode_s - pnn_s + cpu_pnn_s, pnn_s, encode_s, (encode_s - pnn_s + cpu_pnn_s) / encode_s))
