@@ -17,7 +17,7 @@ EXPORTS = (
     'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation', 'pnn_win_flags_device', 'pnn_set_profiling',
     'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused', 'pnn_hevc_best_mode', 'pnn_hevc_best_mode_device',
     'pnn_inspect_net_file', 'pnn_predict_image_blocks_async', 'pnn_synchronize',
-    'pnn_set_hm_cache', 'pnn_hm_cache_stats', 'pnn_set_workspace_budget', 'pnn_register_net',
+    'pnn_set_hm_cache', 'pnn_hm_cache_stats', 'pnn_set_workspace_budget', 'pnn_register_net', 'pnn_set_context_lazy', 'pnn_create_deferred', 'pnn_release_at_exit',
 )
 
 PRECISION_FP32 = 0
@@ -39,6 +39,10 @@ def load():
     vp, i32, i64 = c.c_void_p, c.c_int, c.c_int64
     lib.pnn_create.argtypes = [c.c_char_p, c.c_float, i32, i32, c.POINTER(vp)]
     lib.pnn_create.restype = i32
+    lib.pnn_create_deferred.argtypes = lib.pnn_create.argtypes
+    lib.pnn_create_deferred.restype = i32
+    lib.pnn_release_at_exit.argtypes = [vp]
+    lib.pnn_release_at_exit.restype = i32
     lib.pnn_destroy.argtypes = [vp]
     lib.pnn_destroy.restype = None
     lib.pnn_last_error.argtypes = [vp]
@@ -91,6 +95,8 @@ def load():
     lib.pnn_hevc_best_mode.restype = i32
     lib.pnn_hevc_best_mode_device.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.pnn_hevc_best_mode_device.restype = i32
+    lib.pnn_set_context_lazy.argtypes = [vp, i32]
+    lib.pnn_set_context_lazy.restype = i32
     lib.pnn_set_hm_cache.argtypes = [vp, i32]
     lib.pnn_set_hm_cache.restype = i32
     lib.pnn_hm_cache_stats.argtypes = [vp, c.POINTER(i64), c.POINTER(i64)]

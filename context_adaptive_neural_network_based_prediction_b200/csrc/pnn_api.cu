@@ -17,6 +17,21 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// PNN_TIMING=1: wall-clock trace of the start-up and tear-down steps on stderr (tuning aid)
+struct Trace {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char* what;
+    static bool on() {
+        static const bool v = getenv("PNN_TIMING") && atoi(getenv("PNN_TIMING")) != 0;
+        return v;
+    }
+    explicit Trace(const char* w) : what(w) {}
+    ~Trace() {
+        if (on()) fprintf(stderr, "[pnn timing] %-28s %8.1f ms\n", what,
+                          1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 #define CUDA_TRY(expr)                                                                          \
     do {                                                                                        \
         cudaError_t e_ = (expr);                                                                \
@@ -543,7 +558,9 @@ struct pnn_handle {
     } in_set[2];
     int in_next = 0;
     // HM path
-    int32_t* hm_staged = nullptr;    // pinned, header + 5*64*64 ints
+    int32_t* hm_staged = nullptr;    // page-aligned inside hm_staged_storage, pinned (cudaHostRegister) once the device is up: header + 5*64*64 ints
+    std::vector<int32_t> hm_staged_storage;
+    bool device_ready = false;
     int32_t* hm_out = nullptr;       // pinned, 64*64 ints
     int32_t* d_hm_out_mapped = nullptr;      // device alias of hm_out (mapped pinned memory)
     float* hm_out_raw = nullptr;             // pinned + mapped, 64*64 floats (raw prediction)
@@ -568,6 +585,13 @@ struct pnn_handle {
     cudaEvent_t lane_fork = nullptr, lane_done[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf d_hm_staged;
     int hm_width = 0;
+    struct ContextDesc {                     // arguments of the last pnn_set_context
+        int width = 0, pic_stride = 0, num_intra_neighbor = 0, unit_width = 0, unit_height = 0, above_units = 0, left_units = 0;
+        const int32_t* roi_origin = nullptr;
+        uint8_t flags[2 * 64 + 1];
+    } hm_desc;
+    bool hm_desc_pending = false;            // the pixels of hm_desc are not staged yet (pnn_set_context_lazy)
+    bool hm_lazy_context = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float hm_ms = 0.f;
     // per-kernel profiling
@@ -653,7 +677,13 @@ Net* find_net(pnn_handle* h, int width, int is_fc) {
             // registered earlier, needed now
             const pnn_handle::Pending p = pend->second;
             h->pending.erase(pend);
-            load_flat_file(h, p.graph ? *p.graph : read_flat(p.path));
+            Trace trace("load at first use");
+            FlatFile ff;
+            {
+                Trace t("  read file");
+                if (!p.graph) ff = read_flat(p.path);
+            }
+            load_flat_file(h, p.graph ? *p.graph : ff);
             it = h->nets.find({width, is_fc ? 1 : 0});
         }
     }
@@ -909,6 +939,7 @@ int fail(pnn_handle* h, const std::exception& e) {
 }
 
 void load_flat_file(pnn_handle* h, const FlatFile& ff) {
+    Trace trace(ff.is_fc ? "  upload + tile (FC net)" : "  upload + tile (conv net)");
     persist_stop(h);                          // the persistent kernel holds pointers into the nets
     std::unique_ptr<Net> net(new Net());
     net->W = ff.width;
@@ -945,60 +976,85 @@ extern "C" {
 
 const char* pnn_version(void) { return "libpnn_cuda 0.2 (sm_100a)"; }
 
-int pnn_create(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out) {
+// Everything that touches the GPU at start-up: the device check (there is no CPU fallback), the context, streams, events and
+// the pinned / mapped buffers of the in-loop path.  Run by pnn_create, or by the first call that needs the device after
+// pnn_create_deferred.
+static void init_device(pnn_handle* h) {
+    Trace trace("device initialisation");
+    int count = 0;
+    cudaError_t e;
+    {
+        Trace t("  cudaGetDeviceCount");
+        e = cudaGetDeviceCount(&count);
+    }
+    if (e != cudaSuccess || count == 0) {
+        throw std::runtime_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libpnn_cuda has no CPU fallback)");
+    }
+    const int device = h->device;
+    if (device < 0 || device >= count) throw std::runtime_error("invalid CUDA device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        throw std::runtime_error(std::string("device \"") + prop.name + "\" is not sm_100 (libpnn_cuda is built for sm_100a only)");
+    }
+    {
+        Trace t("  context (cudaFree(0))");
+        CUDA_TRY(cudaFree(0));
+    }
+    h->device_ready = true;                    // from here on pnn_destroy has something to release
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+    for (auto& set : h->in_set) {
+        CUDA_TRY(cudaEventCreateWithFlags(&set.uploaded, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&set.consumed, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming));
+    for (int l = 1; l < 4; ++l) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->lane_done[l], cudaEventDisableTiming));
+    }
+    // (the staging buffer exists already: pnn_set_context may run before the device is needed)
+    CUDA_TRY(cudaHostRegister(h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t), cudaHostRegisterDefault));
+    h->d_splitk.reserve((size_t)64 << 20);
+    CUDA_TRY(cudaHostAlloc((void**)&h->hm_out, 64 * 64 * sizeof(int32_t), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_mapped, h->hm_out, 0));
+    CUDA_TRY(cudaHostAlloc((void**)&h->hm_out_raw, 64 * 64 * sizeof(float), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_raw_mapped, h->hm_out_raw, 0));
+    h->d_hm_staged.reserve((HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t));
+    small_kernels_init();
+    CUDA_TRY(gemm_tc_init());
+}
+
+static void ensure_device(pnn_handle* h) {
+    if (!h->device_ready) init_device(h);
+    CUDA_TRY(cudaSetDevice(h->device));
+}
+
+static int create_impl(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out, bool deferred) {
     if (!out) {
         g_create_error = "`out` is NULL";
         return -1;
     }
     *out = nullptr;
+    Trace trace("pnn_create");
     std::unique_ptr<pnn_handle> h(new pnn_handle());
     try {
         // reference TComPrediction.cpp(substitution):129-133
         if (qp_selection <= 0) {
             throw std::runtime_error("The quantization parameter used for selecting each prediction neural network model is not strictly positive.");
         }
-        int count = 0;
-        cudaError_t e = cudaGetDeviceCount(&count);
-        if (e != cudaSuccess || count == 0) {
-            throw std::runtime_error(std::string("no CUDA device: ") + cudaGetErrorString(e) +
-                                     " (libpnn_cuda has no CPU fallback)");
-        }
-        if (device < 0 || device >= count) throw std::runtime_error("invalid CUDA device ordinal");
-        CUDA_TRY(cudaSetDevice(device));
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-        if (prop.major != 10) {
-            throw std::runtime_error(std::string("device \"") + prop.name + "\" is not sm_100 (libpnn_cuda is built for sm_100a only)");
-        }
         h->device = device;
         h->mean = mean_training;
         if (getenv("PNN_WORKSPACE_GB") && atoi(getenv("PNN_WORKSPACE_GB")) > 0) {
             h->workspace_budget = (size_t)atoi(getenv("PNN_WORKSPACE_GB")) << 30;
         }
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
-        for (auto& set : h->in_set) {
-            CUDA_TRY(cudaEventCreateWithFlags(&set.uploaded, cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&set.consumed, cudaEventDisableTiming));
-        }
-        CUDA_TRY(cudaEventCreate(&h->ev0));
-        CUDA_TRY(cudaEventCreate(&h->ev1));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->lane_fork, cudaEventDisableTiming));
-        for (int l = 1; l < 4; ++l) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
-            CUDA_TRY(cudaEventCreateWithFlags(&h->lane_done[l], cudaEventDisableTiming));
-        }
-        CUDA_TRY(cudaHostAlloc((void**)&h->hm_staged, (HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t), cudaHostAllocMapped));
-        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_staged_mapped, h->hm_staged, 0));
-        h->d_splitk.reserve((size_t)64 << 20);
-        CUDA_TRY(cudaHostAlloc((void**)&h->hm_out, 64 * 64 * sizeof(int32_t), cudaHostAllocMapped));
-        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_mapped, h->hm_out, 0));
-        CUDA_TRY(cudaHostAlloc((void**)&h->hm_out_raw, 64 * 64 * sizeof(float), cudaHostAllocMapped));
-        CUDA_TRY(cudaHostGetDevicePointer((void**)&h->d_hm_out_raw_mapped, h->hm_out_raw, 0));
-        h->d_hm_staged.reserve((HM_HEADER_INTS + 5 * 64 * 64) * sizeof(int32_t));
-        small_kernels_init();
-        CUDA_TRY(gemm_tc_init());
+        h->hm_staged_storage.resize((size_t)HM_HEADER_INTS + 5 * 64 * 64 + 1024);
+        h->hm_staged = (int32_t*)(((uintptr_t)h->hm_staged_storage.data() + 4095) & ~(uintptr_t)4095);
+        if (!deferred) init_device(h.get());
         if (paths_file && paths_file[0]) {
             // reference hevc/hm_common/c++/source_common/tools.cpp:40-110 (parse_file_strings_three_keys):
             // `width,is_pair,0,path`; "pair" models are used when listed and qp_selection >= 32
@@ -1038,6 +1094,24 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
     return 0;
 }
 
+int pnn_create(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out) {
+    return create_impl(paths_file, mean_training, qp_selection, device, out, false);
+}
+
+int pnn_create_deferred(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out) {
+    return create_impl(paths_file, mean_training, qp_selection, device, out, true);
+}
+
+int pnn_release_at_exit(pnn_handle* h) {
+    if (!h) return -1;
+    if (!h->device_ready) return 0;
+    Trace trace("pnn_release_at_exit");
+    cudaSetDevice(h->device);
+    persist_stop(h);
+    cudaDeviceSynchronize();
+    return 0;
+}
+
 int pnn_inspect_net_file(const char* path, int* width_target, int* is_fully_connected, int64_t* n_parameters,
                          double* checksum) {
     try {
@@ -1066,11 +1140,16 @@ int pnn_inspect_net_file(const char* path, int* width_target, int* is_fully_conn
 
 void pnn_destroy(pnn_handle* h) {
     if (!h) return;
+    if (!h->device_ready) {                   // created deferred and never used, or the device initialisation failed early
+        delete h;
+        return;
+    }
+    Trace trace("pnn_destroy");
     cudaSetDevice(h->device);
     persist_stop(h);
     cudaDeviceSynchronize();
     h->nets.clear();
-    if (h->hm_staged) cudaFreeHost(h->hm_staged);
+    if (h->hm_staged) cudaHostUnregister(h->hm_staged);
     if (h->hm_out) cudaFreeHost(h->hm_out);
     if (h->hm_out_raw) cudaFreeHost(h->hm_out_raw);
     if (h->hm_ll) cudaFreeHost((void*)h->hm_ll);
@@ -1100,7 +1179,7 @@ int pnn_load_net(pnn_handle* h, const char* path) {
     Quiesce quiesce(h);
     try {
         if (!path) throw std::runtime_error("`flat_binary_path` is NULL");
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         load_net_impl(h, path);
     } catch (const std::exception& e) {
         return fail(h, e);
@@ -1142,7 +1221,7 @@ int pnn_debug_get_activation(pnn_handle* h, int width, int is_fc, int buffer_ind
         if (elems_per_sample) *elems_per_sample = per;
         if (!out) return 0;
         if (n_samples > net.cap) throw std::runtime_error("more samples requested than the workspace holds");
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         CUDA_TRY(cudaDeviceSynchronize());
         const size_t count = (size_t)n_samples * per;
         const bool split = h->precision == PNN_PRECISION_BF16X3 && !net.buf_fp32_only[buffer_index];
@@ -1173,7 +1252,7 @@ int pnn_hevc_best_mode_device(pnn_handle* h, int width, const uint8_t* d_images,
         if (!d_images || !d_rows || !d_cols) throw std::runtime_error("NULL buffer");
         if (n_images > 1 && !d_idx) throw std::runtime_error("`image_index` is NULL while there are several images");
         check_masks(width, mask_w, mask_h);                       // intraprediction.py:66-72
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         ProfScope ps(h, (cudaStream_t)stream, "hevc_best_mode", n, 35, (int64_t)width * width, false);
         h->launches += launch_hevc_best_mode(d_images, d_idx, d_rows, d_cols, n, height, width_image, width, mask_w, mask_h,
                                              d_best, d_psnr, d_pred, (cudaStream_t)stream);
@@ -1202,7 +1281,7 @@ int pnn_hevc_best_mode(pnn_handle* h, int width, const uint8_t* images, int n_im
             if (idx && (idx[i] < 0 || idx[i] >= n_images)) throw std::runtime_error("`image_index` out of range");
         }
         if (n == 0) return 0;
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         cudaStream_t s = h->stream;
         const size_t img_bytes = (size_t)n_images * height * width_image, px = (size_t)width * width;
         h->d_images.reserve(img_bytes);
@@ -1238,7 +1317,7 @@ int pnn_win_flags_device(pnn_handle* h, const double* d_psnr, const double* d_ba
     Quiesce quiesce(h);
     try {
         if (n < 0 || !d_psnr || !d_base || !d_win) throw std::runtime_error("bad arguments");
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         h->launches += launch_win_flags(d_psnr, d_base, n, d_win, (cudaStream_t)stream);
         CUDA_TRY(cudaGetLastError());
     } catch (const std::exception& e) {
@@ -1270,7 +1349,7 @@ const char* pnn_profile_report(pnn_handle* h, double* gemm_ms, double* gemm_flop
     double g_ms = 0., g_fl = 0., o_ms = 0.;
     int64_t g_n = 0;
     try {
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         CUDA_TRY(cudaDeviceSynchronize());
         struct Agg { int64_t launches = 0; double ms = 0., flops = 0.; };
         std::map<std::string, Agg> agg;
@@ -1313,7 +1392,7 @@ float pnn_debug_time_gemm(pnn_handle* h, int64_t M, int N, int K, int iters, int
     Quiesce quiesce(h);
     try {
         if (M <= 0 || N <= 0 || K <= 0 || N % 16 || K % 8 || iters <= 0) throw std::runtime_error("bad problem size");
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         DevBuf a_hi, a_lo, o_hi, o_lo, wt, bias;
         a_hi.reserve((size_t)M * K * 2);
         a_lo.reserve((size_t)M * K * 2);
@@ -1354,6 +1433,59 @@ int64_t pnn_launch_count(pnn_handle* h) { return h ? h->launches : 0; }
 
 float pnn_last_hm_device_ms(pnn_handle* h) { return h ? h->hm_ms : 0.f; }
 
+// Copies the context described by h->hm_desc into the staging buffer (reference extraction_context.cpp:56-205; masks and
+// mean subtraction follow on the device).
+static void stage_context(pnn_handle* h) {
+    const pnn_handle::ContextDesc& d = h->hm_desc;
+    const int W = d.width, cw = 3 * W;
+    const int32_t* roi_origin = d.roi_origin;
+    const int pic_stride = d.pic_stride, above_units = d.above_units, left_units = d.left_units;
+    const int unit_width = d.unit_width, unit_height = d.unit_height;
+    const uint8_t* flags = d.flags;
+    int32_t* above = h->hm_staged + HM_HEADER_INTS;
+    int32_t* left = above + 3 * W * W;
+    const int total = above_units + left_units + 1;
+    uint32_t lo = 0, hi = 0;
+    int left_rows;
+    if (d.num_intra_neighbor == total) {
+        // extraction_context.cpp:56-90: straight copy
+        const int32_t* p = roi_origin - (int64_t)W * pic_stride - W;
+        for (int i = 0; i < W; ++i, p += pic_stride) memcpy(above + i * cw, p, cw * sizeof(int32_t));
+        p = roi_origin - W;
+        for (int i = 0; i < 2 * W; ++i, p += pic_stride) memcpy(left + i * W, p, W * sizeof(int32_t));
+        for (int u = 0; u < above_units; ++u) (u < 32 ? lo : hi) |= 1u << (u & 31);
+        left_rows = 2 * W;
+        // a unit grid that does not cover the whole portion leaves the rest to the straight copy
+        if (above_units * unit_width < 2 * W) {
+            for (int u = above_units; u * unit_width < 2 * W; ++u) (u < 32 ? lo : hi) |= 1u << (u & 31);
+        }
+    } else {
+        memset(above, 0, 5 * W * W * sizeof(int32_t));
+        // extraction_context.cpp:119-127: the W x W block above-left is always copied
+        const int32_t* p = roi_origin - (int64_t)W * pic_stride - W;
+        for (int i = 0; i < W; ++i, p += pic_stride) memcpy(above + i * cw, p, W * sizeof(int32_t));
+        // extraction_context.cpp:149-166
+        for (int u = 0; u < above_units; ++u) {
+            if (!flags[left_units + 1 + u]) continue;
+            (u < 32 ? lo : hi) |= 1u << (u & 31);
+            const int32_t* q = roi_origin - (int64_t)W * pic_stride + u * unit_width;
+            int32_t* dst = above + W + u * unit_width;
+            for (int j = 0; j < W; ++j, q += pic_stride, dst += cw) memcpy(dst, q, unit_width * sizeof(int32_t));
+        }
+        // extraction_context.cpp:189-205: source and destination advance only on available units
+        int n_left = 0;
+        for (int u = 0; u < left_units; ++u) n_left += flags[left_units - 1 - u] ? 1 : 0;
+        left_rows = n_left * unit_height;
+        p = roi_origin - W;
+        for (int i = 0; i < left_rows; ++i, p += pic_stride) memcpy(left + i * W, p, W * sizeof(int32_t));
+    }
+    h->hm_staged[0] = (int32_t)lo;
+    h->hm_staged[1] = (int32_t)hi;
+    h->hm_staged[2] = unit_width;
+    h->hm_staged[3] = left_rows;
+    h->hm_desc_pending = false;
+}
+
 int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic_stride, const uint8_t* flags,
                     int num_intra_neighbor, int unit_width, int unit_height, int above_units, int left_units) {
     if (!h) return -1;
@@ -1365,61 +1497,37 @@ int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic
         if (width != 4 && width != 8 && width != 16 && width != 32 && width != 64) {
             throw std::runtime_error("the width of the TB does not belong to {4, 8, 16, 32, 64}");
         }
-        if (unit_width <= 0 || unit_height <= 0 || above_units <= 0 || left_units <= 0 || above_units > 64 ||
+        if (unit_width <= 0 || unit_height <= 0 || above_units <= 0 || left_units <= 0 || above_units > 64 || left_units > 64 ||
             above_units * unit_width > 2 * width || left_units * unit_height > 2 * width) {
             throw std::runtime_error("inconsistent neighbouring unit description");
         }
-        const int W = width, cw = 3 * W;
-        int32_t* above = h->hm_staged + HM_HEADER_INTS;
-        int32_t* left = above + 3 * W * W;
-        const int total = above_units + left_units + 1;
-        uint32_t lo = 0, hi = 0;
-        int left_rows;
-        if (num_intra_neighbor == total) {
-            // extraction_context.cpp:56-90: straight copy
-            const int32_t* p = roi_origin - (int64_t)W * pic_stride - W;
-            for (int i = 0; i < W; ++i, p += pic_stride) memcpy(above + i * cw, p, cw * sizeof(int32_t));
-            p = roi_origin - W;
-            for (int i = 0; i < 2 * W; ++i, p += pic_stride) memcpy(left + i * W, p, W * sizeof(int32_t));
-            for (int u = 0; u < above_units; ++u) (u < 32 ? lo : hi) |= 1u << (u & 31);
-            left_rows = 2 * W;
-            // a unit grid that does not cover the whole portion leaves the rest to the straight copy
-            if (above_units * unit_width < 2 * W) {
-                for (int u = above_units; u * unit_width < 2 * W; ++u) (u < 32 ? lo : hi) |= 1u << (u & 31);
-            }
-        } else {
-            memset(above, 0, 5 * W * W * sizeof(int32_t));
-            // extraction_context.cpp:119-127: the W x W block above-left is always copied
-            const int32_t* p = roi_origin - (int64_t)W * pic_stride - W;
-            for (int i = 0; i < W; ++i, p += pic_stride) memcpy(above + i * cw, p, W * sizeof(int32_t));
-            // extraction_context.cpp:133-138
-            if (!flags[left_units]) {
-                throw std::runtime_error("The neighbouring unit above and on the left side of the current TB is not available.");
-            }
-            // extraction_context.cpp:149-166
-            for (int u = 0; u < above_units; ++u) {
-                if (!flags[left_units + 1 + u]) continue;
-                (u < 32 ? lo : hi) |= 1u << (u & 31);
-                const int32_t* q = roi_origin - (int64_t)W * pic_stride + u * unit_width;
-                int32_t* d = above + W + u * unit_width;
-                for (int j = 0; j < W; ++j, q += pic_stride, d += cw) memcpy(d, q, unit_width * sizeof(int32_t));
-            }
-            // extraction_context.cpp:189-205: source and destination advance only on available units
-            int n_left = 0;
-            for (int u = 0; u < left_units; ++u) n_left += flags[left_units - 1 - u] ? 1 : 0;
-            left_rows = n_left * unit_height;
-            p = roi_origin - W;
-            for (int i = 0; i < left_rows; ++i, p += pic_stride) memcpy(left + i * W, p, W * sizeof(int32_t));
+        // extraction_context.cpp:133-138
+        if (num_intra_neighbor != above_units + left_units + 1 && !flags[left_units]) {
+            throw std::runtime_error("The neighbouring unit above and on the left side of the current TB is not available.");
         }
-        h->hm_width = W;
-        h->hm_staged[0] = (int32_t)lo;
-        h->hm_staged[1] = (int32_t)hi;
-        h->hm_staged[2] = unit_width;
-        h->hm_staged[3] = left_rows;
+        pnn_handle::ContextDesc& d = h->hm_desc;
+        d.width = width;
+        d.roi_origin = roi_origin;
+        d.pic_stride = pic_stride;
+        d.num_intra_neighbor = num_intra_neighbor;
+        d.unit_width = unit_width;
+        d.unit_height = unit_height;
+        d.above_units = above_units;
+        d.left_units = left_units;
+        memcpy(d.flags, flags, (size_t)(above_units + left_units + 1));
+        h->hm_desc_pending = true;
+        h->hm_width = width;
+        if (!h->hm_lazy_context) stage_context(h);   // lazy: pnn_predict_hm copies the pixels, if it is ever called
     } catch (const std::exception& e) {
         h->hm_width = 0;
         return fail(h, e);
     }
+    return 0;
+}
+
+int pnn_set_context_lazy(pnn_handle* h, int enabled) {
+    if (!h) return -1;
+    h->hm_lazy_context = enabled != 0;
     return 0;
 }
 
@@ -1772,9 +1880,10 @@ int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
     try {
         if (!dst) throw std::runtime_error("`piPred` is NULL.");
         if (h->hm_width != width) throw std::runtime_error("pnn_predict_hm called without a matching pnn_set_context");
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         Net& net = hm_net(h, width);
         const int W = width;
+        if (h->hm_desc_pending) stage_context(h);
         run_hm(h, net);
         // reference TComPrediction.cpp(substitution):626-635: row-major copy with HM's stride
         for (int i = 0; i < W; ++i) memcpy(dst + (int64_t)i * dst_stride, h->hm_out + i * W, W * sizeof(int32_t));
@@ -1791,7 +1900,7 @@ int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat,
         if (width != 4 && width != 8 && width != 16 && width != 32 && width != 64) {
             throw std::runtime_error("the width of the TB does not belong to {4, 8, 16, 32, 64}");
         }
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         Net& net = hm_net(h, width);
         const int W = width;
         // a convolutional net serving widths 4 / 8 reads its two portions from the two halves of the flattened context
@@ -1807,6 +1916,7 @@ int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat,
             memcpy(px + 3 * W * W, left, (size_t)2 * W * W * sizeof(float));
         }
         h->hm_width = 0;                                       // a staged pnn_set_context is consumed
+        h->hm_desc_pending = false;
         run_hm(h, net);
         memcpy(out, h->hm_out_raw, (size_t)W * W * sizeof(float));
     } catch (const std::exception& e) {
@@ -1846,7 +1956,7 @@ int pnn_predict_batch_device(pnn_handle* h, int width, int is_fc, const float* d
     try {
         if (n < 0) throw std::runtime_error("negative number of predictions");
         if (!d_a || !d_out || (!is_fc && !d_l)) throw std::runtime_error("NULL buffer");
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         batch_device(h, *find_net(h, width, is_fc), d_a, d_l, n, d_out, (cudaStream_t)stream);
     } catch (const std::exception& e) {
         return fail(h, e);
@@ -1861,7 +1971,7 @@ int pnn_predict_batch(pnn_handle* h, int width, int is_fc, const float* a, const
         if (n < 0) throw std::runtime_error("negative number of predictions");
         if (n == 0) return 0;
         if (!a || !out || (!is_fc && !l)) throw std::runtime_error("NULL buffer");
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         Net& net = *find_net(h, width, is_fc);
         const int64_t px = (int64_t)width * width;
         const int64_t na = is_fc ? 5 * px : 3 * px;
@@ -1899,7 +2009,7 @@ int pnn_predict_image_blocks_device(pnn_handle* h, int width, int is_fc, const u
         if (!d_images || !d_rows || !d_cols) throw std::runtime_error("NULL buffer");
         if (n_images > 1 && !d_idx) throw std::runtime_error("`image_index` is NULL while there are several images");
         check_masks(width, mask_w, mask_h);
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         image_blocks_device(h, *find_net(h, width, is_fc), d_images, height, width_image, d_idx, d_rows, d_cols, n, mask_w,
                             mask_h, d_f32, d_u8, d_psnr, (cudaStream_t)stream);
     } catch (const std::exception& e) {
@@ -1929,7 +2039,7 @@ static int image_blocks_host(pnn_handle* h, int width, int is_fc, const uint8_t*
             if (idx && (idx[i] < 0 || idx[i] >= n_images)) throw std::runtime_error("`image_index` out of range");
         }
         if (n == 0) return 0;
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         Net& net = *find_net(h, width, is_fc);
         const int64_t px = (int64_t)width * width;
         cudaStream_t s = h->stream;
@@ -2008,7 +2118,7 @@ int pnn_synchronize(pnn_handle* h) {
     if (!h) return -1;
     Quiesce quiesce(h);
     try {
-        CUDA_TRY(cudaSetDevice(h->device));
+        ensure_device(h);
         CUDA_TRY(cudaStreamSynchronize(h->stream_in));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream_out));

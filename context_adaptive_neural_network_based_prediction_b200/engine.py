@@ -34,14 +34,14 @@ class Engine(object):
     HM (TComPrediction.cpp:108-236).
     """
 
-    def __init__(self, mean_training=MEAN_TRAINING_LUMINANCE, device=0, paths_file=None, qp_selection=22):
+    def __init__(self, mean_training=MEAN_TRAINING_LUMINANCE, device=0, paths_file=None, qp_selection=22, deferred=False):
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         self._pending = []                      # arrays of enqueued asynchronous calls, kept alive until synchronize()
         self.mean_training = float(mean_training)
         path = paths_file.encode() if paths_file else None
-        if self._lib.pnn_create(path, ctypes.c_float(self.mean_training), int(qp_selection), int(device),
-                                ctypes.byref(self._h)) != 0:
+        create = self._lib.pnn_create_deferred if deferred else self._lib.pnn_create   # deferred: the GPU is touched at first use
+        if create(path, ctypes.c_float(self.mean_training), int(qp_selection), int(device), ctypes.byref(self._h)) != 0:
             raise PnnError(self._lib.pnn_last_error(None).decode())
 
     def close(self):
@@ -83,6 +83,10 @@ class Engine(object):
     def set_hm_fused(self, enabled):
         """In-loop nets: persistent shared-memory-resident FC kernel + split-K conv graphs (default) or plain CUDA graphs."""
         self._check(self._lib.pnn_set_hm_fused(self._h, int(bool(enabled))))
+
+    def set_context_lazy(self, enabled):
+        """pnn_set_context records its arguments only; pnn_predict_hm copies the pixels (C ABI pnn_set_context_lazy)."""
+        self._check(self._lib.pnn_set_context_lazy(self._h, int(bool(enabled))))
 
     def set_hm_cache(self, enabled):
         """Memo of in-loop results keyed by the exact context (C ABI pnn_set_hm_cache); off by default."""

@@ -53,4 +53,36 @@ for V in $VARIANTS; do
     echo "built $OUT/TAppEncoderStatic_${V}_cpu and $OUT/TAppDecoderStatic_${V}_cpu (CPU baseline backend)"
   fi
 done
+# Direct binding (hm/direct/): the three hook files are patched copies made under /tmp by
+# hm/direct/patch_hm.py, everything else compiles from the reference tree as it lies -> *_direct executables
+for V in $VARIANTS; do
+  [ "$V" = "regular" ] && continue
+  [ "${DIRECT:-1}" = "1" ] || continue
+  SRC="$REF/hevc/hm_16_15_$V/source"
+  COMMON="$REF/hevc/hm_common/c++/source_common"
+  OBJ="/tmp/pnn_hm_build/${V}_direct"
+  # a mirror of the source tree made of symbolic links (quote-includes resolve next to the including file, so the
+  # patched header must sit among its neighbours), with the three hook files replaced by their patched copies
+  MIRROR="$OBJ/mirror"
+  rm -rf "$MIRROR"
+  mkdir -p "$OBJ"
+  cp -rs "$SRC" "$MIRROR"
+  rm -f "$MIRROR/Lib/TLibCommon/TComPrediction.h" "$MIRROR/Lib/TLibCommon/TComPrediction.cpp" "$MIRROR/Lib/TLibCommon/TComPattern.cpp"
+  python "$ROOT/hm/direct/patch_hm.py" "$SRC/Lib/TLibCommon" "$MIRROR/Lib/TLibCommon" || exit 1
+  SRC="$MIRROR"
+  FLAGS="-O3 -std=c++11 -DMSYS_LINUX -w -include cmath -I$ROOT/hm/direct -I$ROOT/include -I$SRC/Lib -I$SRC/Lib/TLibCommon -I$COMMON"
+  LIBSRCS=$(ls $SRC/Lib/TLibCommon/*.cpp $SRC/Lib/TLibVideoIO/*.cpp $SRC/Lib/TLibEncoder/*.cpp $SRC/Lib/TLibDecoder/*.cpp $SRC/Lib/TAppCommon/*.cpp)
+  LIBSRCS="$LIBSRCS $COMMON/extraction_context.cpp $COMMON/tools.cpp $COMMON/visualization_debugging.cpp $ROOT/hm/direct/pnn_hm_direct.cpp"
+  ENCSRCS=$(ls $SRC/App/TAppEncoder/*.cpp)
+  DECSRCS=$(ls $SRC/App/TAppDecoder/*.cpp)
+  export FLAGS OBJ
+  printf '%s\n' $LIBSRCS | xargs -P "$JOBS" -I{} bash -c 'compile {} lib'
+  printf '%s\n' $ENCSRCS | xargs -P "$JOBS" -I{} bash -c 'compile {} enc'
+  printf '%s\n' $DECSRCS | xargs -P "$JOBS" -I{} bash -c 'compile {} dec'
+  gcc -O3 -w -c "$SRC/Lib/libmd5/libmd5.c" -o "$OBJ/lib_libmd5.o"
+  LINK="-L$PKG/csrc -lpnn_cuda -Wl,-rpath,\$ORIGIN/../../context_adaptive_neural_network_based_prediction_b200/csrc -lpthread -ldl"
+  g++ -o "$OUT/TAppEncoderStatic_${V}_direct" $OBJ/enc_*.o $OBJ/lib_*.o $LINK
+  g++ -o "$OUT/TAppDecoderStatic_${V}_direct" $OBJ/dec_*.o $OBJ/lib_*.o $LINK
+  echo "built $OUT/TAppEncoderStatic_${V}_direct and $OUT/TAppDecoderStatic_${V}_direct (direct binding)"
+done
 cp "$REF/hevc/configuration/intra_main_rext.cfg" "$OUT/intra_main_rext.cfg"

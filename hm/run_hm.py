@@ -18,10 +18,11 @@ ap.add_argument('--height', type=int, default=1080)
 ap.add_argument('--qps', default='22,27,32,37')
 ap.add_argument('--variant', default='substitution')
 ap.add_argument('--seed', type=int, default=0)
-ap.add_argument('--backend', default='cuda', choices=('cuda', 'cpu', 'null'),
-                help='cuda: libpnn_cuda (the product); cpu: the *_cpu executables = same codec objects linked against '
+ap.add_argument('--backend', default='cuda', choices=('cuda', 'direct', 'cpu', 'null'),
+                help='cuda: libpnn_cuda through the link seam hm/shim (only Session::Run replaced); direct: libpnn_cuda through the patched hooks of hm/direct (gather and epilogue in the library too); cpu: the *_cpu executables = same codec objects linked against '
                      'oracle/_ref/libpnn_ref.so (libtorch-CPU stand-in for the TensorFlow-CPU build, the baseline leg); '
                      'null: the same with PNN_REF_NULL=1 (predictions are zeros at once: the codec\'s own time)')
+ap.add_argument('--ref-threads', default='', help='cpu backend: intra-op threads "fc,conv" (default: all cores for both)')
 ap.add_argument('--keep', default='', help='directory that receives the bitstreams and reconstructions (for rd_compare)')
 ap.add_argument('--image', default='', help='.npy uint8 luminance image instead of the synthetic frame')
 ap.add_argument('--trained-small-nets', action='store_true',
@@ -32,11 +33,13 @@ ap.add_argument('--frozen-graphs', action='store_true',
 args = ap.parse_args()
 
 build = os.path.join(ROOT, 'hm', '_build')
-suffix = '' if args.backend == 'cuda' or args.variant == 'regular' else '_cpu'
+suffix = '' if args.backend == 'cuda' or args.variant == 'regular' else ('_direct' if args.backend == 'direct' else '_cpu')
 enc = os.path.join(build, 'TAppEncoderStatic_' + args.variant + suffix)
 dec = os.path.join(build, 'TAppDecoderStatic_' + args.variant + suffix)
 if args.backend == 'null':
     os.environ['PNN_REF_NULL'] = '1'
+if args.ref_threads:
+    os.environ['PNN_REF_THREADS_FC'], os.environ['PNN_REF_THREADS_CONV'] = args.ref_threads.split(',')
 cfg = os.path.join(build, 'intra_main_rext.cfg')
 tmp = tempfile.mkdtemp(prefix='pnn_hm_')
 if args.keep:
@@ -79,6 +82,8 @@ for qp in [int(q) for q in args.qps.split(',')]:
     t0 = time.time()
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
     t_enc = time.time() - t0
+    if os.environ.get('PNN_TIMING'):
+        sys.stderr.write('--- encoder\n' + p.stderr)
     if p.returncode != 0:
         print(json.dumps({'qp': qp, 'error': 'encoder failed', 'stderr': p.stderr[-800:], 'stdout': p.stdout[-400:]}))
         continue
@@ -91,11 +96,13 @@ for qp in [int(q) for q in args.qps.split(',')]:
     d = subprocess.run([dec, '-b', bit, '-o', rec_d, '-d', '8'] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                        env=dict(os.environ, PNN_HM_STATS=stats_d))
     t_dec = time.time() - t0
+    if os.environ.get('PNN_TIMING'):
+        sys.stderr.write('--- decoder\n' + d.stderr)
     dec_total = re.findall(r'Total Time:\s+([0-9.]+) sec', d.stdout)
     same = os.path.exists(rec_e) and os.path.exists(rec_d) and open(rec_e, 'rb').read() == open(rec_d, 'rb').read()
     print(json.dumps({
         'config': 'configs[3]: HM-16.15 %s, first-frame intra, %s %dx%d 4:0:0, intra_main_rext.cfg' % (args.variant, os.path.basename(args.image) if args.image else 'synthetic', args.width, args.height),
-        'backend': args.backend, 'host_cores': os.cpu_count(),
+        'backend': args.backend, 'host_cores': os.cpu_count(), 'ref_threads': args.ref_threads,
         'trained_small_nets': args.trained_small_nets, 'qp': qp, 'encoder_wall_s': t_enc, 'encoder_total_time_s': float(enc_total[0]) if enc_total else None,
         'decoder_wall_s': t_dec, 'decoder_total_time_s': float(dec_total[0]) if dec_total else None,
         'bytes': int(bits[0]) if bits else None, 'y_psnr_kbps': psnr[0] if psnr else None,

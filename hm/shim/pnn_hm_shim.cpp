@@ -36,7 +36,7 @@ void print_stats() {
     }
     if (f != stderr) fclose(f);
     if (g_handle) {
-        pnn_destroy(g_handle);
+        pnn_release_at_exit(g_handle);      // the process ends here: no buffer-by-buffer teardown
         g_handle = NULL;
     }
 }
@@ -49,7 +49,7 @@ pnn_handle* handle() {
         int device(0);
         const char* env = getenv("PNN_DEVICE");
         if (env) device = atoi(env);
-        if (pnn_create(NULL, 0.f, 1, device, &g_handle) != 0) {
+        if (pnn_create_deferred(NULL, 0.f, 1, device, &g_handle) != 0) {
             fprintf(stderr, "%s\n", pnn_last_error(NULL));
             return NULL;
         }

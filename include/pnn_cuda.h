@@ -49,8 +49,23 @@ enum {
  */
 int pnn_create(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out);
 
+/*
+ * Same, but nothing touches the GPU yet: the paths file and the headers of the weight files are validated at once, the
+ * device check, the CUDA context and every buffer wait for the first call that needs them (which then fails loudly if there
+ * is no sm_100 device).  For short-lived processes: a decoder whose bitstream never uses the neural-network mode finishes
+ * without paying the ~1-2 s of CUDA start-up.  What the HM bindings use.
+ */
+int pnn_create_deferred(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out);
+
 /* Replaces std::unique_ptr<tensorflow::Session> teardown. */
 void pnn_destroy(pnn_handle* h);
+
+/*
+ * For a process that is about to exit: stops the persistent kernel and waits for the device, but frees nothing (releasing
+ * hundreds of device buffers one by one costs seconds; process exit returns them at once).  The handle must not be used
+ * afterwards.
+ */
+int pnn_release_at_exit(pnn_handle* h);
 
 /* Last error message of the handle (or of the failed pnn_create when h is NULL). */
 const char* pnn_last_error(pnn_handle* h);
@@ -98,6 +113,15 @@ int pnn_set_precision(pnn_handle* h, int precision);
 int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic_stride,
                     const uint8_t* neighbor_flags, int num_intra_neighbor,
                     int unit_width, int unit_height, int above_units, int left_units);
+
+/*
+ * 1: pnn_set_context only records its arguments (after the same checks) and pnn_predict_hm copies the context pixels,
+ * so a context that is never predicted from costs nothing -- HM extracts one for every transform block and every
+ * candidate mode (TEncSearch.cpp(substitution):1229-1235), the neural-network mode needs few of them.  The caller then
+ * guarantees that the reconstruction plane and `roi_origin` stay unchanged between the two calls, which holds in HM
+ * (prediction precedes reconstruction).  0 (default): pixels are copied by pnn_set_context.
+ */
+int pnn_set_context_lazy(pnn_handle* h, int enabled);
 
 /*
  * Step 2 of the in-loop call: the neural-network branch of TComPrediction::predIntraAng

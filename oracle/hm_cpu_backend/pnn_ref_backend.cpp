@@ -209,6 +209,9 @@ struct pnn_handle {
     std::string error;
     std::map<std::pair<int, int>, std::unique_ptr<RefNet>> nets;
     bool null_backend = false;
+    // intra-op threads per kind of net (PNN_REF_THREADS_FC / PNN_REF_THREADS_CONV, else PNN_REF_THREADS, else all cores):
+    // the baseline is given the setting that is fastest on the box (tools/ref_backend_latency.py sweeps it)
+    int threads_fc = 0, threads_conv = 0, threads_now = 0;
 };
 
 extern "C" {
@@ -232,13 +235,24 @@ int pnn_create(const char* paths_file, float, int qp_selection, int, pnn_handle*
     pnn_handle* h = new pnn_handle();
     const char* e = getenv("PNN_REF_NULL");
     h->null_backend = e && atoi(e) != 0;
-    const char* t = getenv("PNN_REF_THREADS");
-    if (t && atoi(t) > 0) at::set_num_threads(atoi(t));
+    auto env_int = [](const char* name) {
+        const char* v = getenv(name);
+        return v && atoi(v) > 0 ? atoi(v) : 0;
+    };
+    const int all = env_int("PNN_REF_THREADS");
+    h->threads_fc = env_int("PNN_REF_THREADS_FC") ? env_int("PNN_REF_THREADS_FC") : all;
+    h->threads_conv = env_int("PNN_REF_THREADS_CONV") ? env_int("PNN_REF_THREADS_CONV") : all;
     *out = h;
     return 0;
 }
 
 void pnn_destroy(pnn_handle* h) { delete h; }
+
+int pnn_create_deferred(const char* paths_file, float mean, int qp_selection, int device, pnn_handle** out) {
+    return pnn_create(paths_file, mean, qp_selection, device, out);
+}
+
+int pnn_release_at_exit(pnn_handle*) { return 0; }
 
 const char* pnn_last_error(pnn_handle* h) { return h ? h->error.c_str() : g_error.c_str(); }
 
@@ -283,6 +297,14 @@ int pnn_hm_cache_stats(pnn_handle*, int64_t* hits, int64_t* misses) {
     return 0;
 }
 
+// baseline-only helper (tools/ref_backend_latency.py): intra-op threads of the FC / convolutional nets
+int pnn_ref_set_threads(pnn_handle* h, int threads_fc, int threads_conv) {
+    if (!h) return -1;
+    h->threads_fc = threads_fc;
+    h->threads_conv = threads_conv;
+    return 0;
+}
+
 int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat, const float* left, float* out) {
     if (!h) return -1;
     try {
@@ -296,6 +318,11 @@ int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat,
             return 0;
         }
         if (!net.is_fc && !left) left = above_or_flat + 3 * width * width;
+        const int want = net.is_fc ? h->threads_fc : h->threads_conv;
+        if (want > 0 && want != h->threads_now) {
+            at::set_num_threads(want);
+            h->threads_now = want;
+        }
         const at::Tensor y = forward(net, above_or_flat, left);
         memcpy(out, y.data_ptr<float>(), (size_t)width * width * sizeof(float));
     } catch (const std::exception& e) {

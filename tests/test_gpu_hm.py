@@ -325,3 +325,32 @@ def test_registered_nets_load_at_first_use(weights_dir):
             eng.register_net(truncated)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize('width', [8, 16])
+def test_lazy_context_staging_gives_the_same_prediction(engine, weights_dir, width):
+    """pnn_set_context_lazy: the pixels are copied by pnn_predict_hm instead of pnn_set_context (HM extracts a context for
+    every transform block and candidate mode, the NN mode needs few of them); same checks, same prediction."""
+    from context_adaptive_neural_network_based_prediction_b200 import PnnError
+    is_fc = width <= 8
+    path, _ = helpers.make_net_file(weights_dir, width, is_fc, seed=250 + width, gain=helpers.GAIN[(width, is_fc)])
+    engine.load_net(path)
+    plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 31).astype(numpy.int32)
+    units = 2 * width // 4
+    flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+    flags[:units // 2] = 0
+    n_avail = int(flags.sum())
+    engine.set_context(width, plane, width + 2, width + 4, flags, n_avail)
+    eager = engine.predict_hm(width).copy()
+    try:
+        engine.set_context_lazy(True)
+        engine.set_context(width, plane, width + 2, width + 4, flags, n_avail)
+        lazy = engine.predict_hm(width).copy()
+        bad = flags.copy(); bad[units] = 0                          # above-left unavailable: refused at set_context time
+        with pytest.raises(PnnError):
+            engine.set_context(width, plane, width + 2, width + 4, bad, n_avail - 1)
+        with pytest.raises(PnnError):
+            engine.predict_hm(width)                                # the failed set_context left nothing staged
+    finally:
+        engine.set_context_lazy(False)
+    numpy.testing.assert_array_equal(eager, lazy)
