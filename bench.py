@@ -1,12 +1,14 @@
 """Benchmark of the PNN hot path (BASELINE.json configs[1]).
 
-Workload (per GPU; "scaling": "weak"): 100 synthetic BSDS-shaped 320x480 luminance images, every
-W-aligned block with an in-image context anchor, for W in {4, 8, 16, 32} (nets FC-4, FC-8, CONV-16,
-CONV-32, seeded random init -- the pretrained HM weights are not shipped with the reference), outputs =
-rounded uint8 predictions, per-block PSNR (float64) and win flag against a supplied baseline PSNR array;
-ONE gather of the statistics to rank 0.  A "step" is one pass over all four block sizes.
+Workload: 100 synthetic BSDS-shaped 320x480 luminance images, every W-aligned block with an in-image context
+anchor, for W in {4, 8, 16, 32} (nets FC-4, FC-8, CONV-16, CONV-32, seeded random init -- the pretrained HM
+weights are not shipped with the reference), outputs = rounded uint8 predictions, per-block PSNR (float64) and win
+flag against a supplied baseline PSNR array; ONE gather of the statistics to rank 0.  A "step" is one pass over
+all four block sizes.  `--scaling strong` (default, what BASELINE.json states: the 100 images are sharded round-robin
+over the N GPUs) or `--scaling weak` (100 images per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong|weak]
+    python bench.py --config conv64 | hm       (builder-run records of BASELINE.json configs[2] / configs[3])
 
 `value`  : predictions/s with images and block lists resident in HBM (device-pointer C-ABI calls).
 `e2e`    : the same metric through the host-pointer C-ABI call (pinned host buffers; H2D of the images
@@ -32,7 +34,7 @@ if ROOT not in sys.path:
 WIDTHS = ((4, True), (8, True), (16, False), (32, False))
 N_IMAGES, HEIGHT, WIDTH_IMAGE = 100, 320, 480
 MEAN = 117.8952234192841
-METRIC = 'PNN predictions/sec (4x4+8x8+16x16+32x32 blocks, 100 BSDS-shaped images per GPU)'
+METRIC = 'PNN predictions/sec (4x4+8x8+16x16+32x32 blocks of 100 BSDS-shaped images)'
 # algorithmic FLOPs per prediction = 2 * MACs (dense count)
 MACS = {4: 2995200, 8: 3340800, 16: 48750592, 32: 273317888}
 
@@ -57,17 +59,21 @@ def synthetic_image(height, width, seed):
     return numpy.clip(numpy.round(img), 0, 255).astype(numpy.uint8)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, scaling='strong'):
+    """-> (config dict, blocks of the WHOLE job per width)."""
     from context_adaptive_neural_network_based_prediction_b200 import offline
-    blocks = {w: len(offline.grid_blocks(HEIGHT, WIDTH_IMAGE, w)[0]) * N_IMAGES for w, _ in WIDTHS}
+    n_images = N_IMAGES if scaling == 'strong' else N_IMAGES * n_gpus
+    blocks = {w: len(offline.grid_blocks(HEIGHT, WIDTH_IMAGE, w)[0]) * n_images for w, _ in WIDTHS}
     return {
         'workload': 'configs[1]: PNN 4x4/8x8/16x16/32x32 batched prediction over 100 synthetic BSDS-shaped '
-                    '(320x480 after the reference 1-px crop) images per GPU, PSNR / win statistics gathered',
-        'images_per_gpu': N_IMAGES, 'image_shape': [HEIGHT, WIDTH_IMAGE],
+                    '(320x480 after the reference 1-px crop) images, PSNR / win statistics gathered',
+        'scaling_mode': 'strong: 100 images in total, image i on rank i % N (offline.shard_image_indices)' if scaling == 'strong'
+                        else 'weak: 100 images per GPU',
+        'images_total': n_images, 'image_shape': [HEIGHT, WIDTH_IMAGE],
         'nets': ['FC-4', 'FC-8', 'CONV-16', 'CONV-32'], 'weights': 'seeded random init (reference initialisers)',
-        'blocks_per_gpu': {str(w): n for w, n in blocks.items()}, 'masks': [0, 0],
+        'blocks_total': {str(w): n for w, n in blocks.items()}, 'masks': [0, 0],
         'parallelism': 'images sharded over %d GPU(s), no data-path collective, one NCCL gather of statistics' % n_gpus,
-        'l2': 'explicit flush (256 MiB write) before every timed step; per-step activations (>10 GB) exceed the 126 MB L2 anyway',
+        'l2': 'explicit flush (256 MiB write) before every timed step; per-step activations (GBs) exceed the 126 MB L2 anyway',
     }, blocks
 
 
@@ -170,14 +176,17 @@ def aggregate_rate(rates, blocks):
 def run_reference(args, rank):
     if rank != 0:
         return
-    cfg, blocks = workload_config(args.gpus)
+    cfg, blocks = workload_config(args.gpus, args.scaling)
     tmp = tempfile.mkdtemp(prefix='pnn_bench_')
     _, tensors = make_weights(tmp)
-    cpu_reference_rates(tensors, 0.5)                         # warm-up
-    values, counts = [], {}
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_reference_rates(tensors, 0.3)                     # warm-up
+    values, counts, step_seconds = [], {}, []
     t_all = time.perf_counter()
     for _ in range(max(1, args.steps)):
+        t_step = time.perf_counter()
         rates, counts = cpu_reference_rates(tensors, args.reference_seconds)
+        step_seconds.append(time.perf_counter() - t_step)
         values.append(aggregate_rate(rates, blocks))
     value = float(numpy.mean(values))
     cores = os.cpu_count() or 1
@@ -185,8 +194,11 @@ def run_reference(args, rank):
               'full block mix' % {str(k): v for k, v in counts.items()})
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'predictions/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * sum(blocks.values()) / value,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        # a step of this arm is a BOUNDED SAMPLE of the workload (its measured wall time is `ms_per_step`); `value` is the
+        # measured rate of the sample, weighted by the block mix of the full workload
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * float(numpy.mean(step_seconds)),
+        'ms_full_workload_at_this_rate': 1e3 * sum(blocks.values()) / value,
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': cfg,
         'cpu_baseline': {'value': value, 'unit': 'predictions/s', 'cores': cores, 'kind': 'port', 'sample': sample,
                          'note': 'TensorFlow 1.x is not installable offline; the fp32 oracle on torch-CPU (oneDNN/MKL) stands in '
@@ -207,6 +219,10 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'],
+                    help='strong (BASELINE.json configs[1]): 100 images in total sharded over the GPUs; weak: 100 images per GPU')
+    ap.add_argument('--config', default='offline', choices=['offline', 'conv64', 'hm'],
+                    help='offline = BASELINE.json configs[1] (the driver\'s bench); conv64 = configs[2]; hm = configs[3]')
     ap.add_argument('--reference-seconds', type=float, default=3.0, help='CPU seconds per block size per step')
     ap.add_argument('--cpu-baseline-seconds', type=float, default=4.0)
     ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'fp32'])
@@ -224,6 +240,11 @@ def main():
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
 
+    if args.config != 'offline':
+        if rank == 0:
+            import bench_configs
+            (bench_configs.run_conv64 if args.config == 'conv64' else bench_configs.run_hm)(args, emit)
+        return
     if args.impl == 'reference':
         run_reference(args, rank)
         return
@@ -239,7 +260,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     args.warmup = max(args.warmup, 3)
-    cfg, blocks = workload_config(world)
+    cfg, blocks = workload_config(world, args.scaling)
     tmp = tempfile.mkdtemp(prefix='pnn_bench_')
     paths, tensors = make_weights(tmp)
     eng = Engine(mean_training=MEAN, device=local_rank)
@@ -247,19 +268,29 @@ def main():
         eng.load_net(paths[w])
     eng.set_precision(args.precision)
 
-    # this rank's image shard: images rank*100 .. rank*100+99 of the (weak-scaling) image set
-    images_np = numpy.stack([synthetic_image(HEIGHT, WIDTH_IMAGE, rank * N_IMAGES + i) for i in range(N_IMAGES)])
+    # this rank's image shard.  strong: image i of the 100 lives on rank i % N (13 or 12 images per rank at N = 8);
+    # weak: images rank*100 .. rank*100+99 of a 100*N image set
+    if args.scaling == 'strong':
+        seeds_of = [offline.shard_image_indices(N_IMAGES, r, world) for r in range(world)]
+    else:
+        seeds_of = [list(range(r * N_IMAGES, (r + 1) * N_IMAGES)) for r in range(world)]
+    n_local = len(seeds_of[rank])
+    blocks_per_image = sum(len(offline.grid_blocks(HEIGHT, WIDTH_IMAGE, w)[0]) for w, _ in WIDTHS)
+    counts = [len(sd) * blocks_per_image for sd in seeds_of]              # blocks per rank, known to everybody
+    ragged = len(set(counts)) > 1
+    images_np = numpy.stack([synthetic_image(HEIGHT, WIDTH_IMAGE, sd) for sd in seeds_of[rank]])
     images_pin = torch.from_numpy(images_np).pin_memory()
     d_images = images_pin.to(dev)
-    total = sum(blocks.values())
+    total_job = sum(blocks.values())
+    total = counts[rank]
     d_psnr = torch.empty(total, dtype=torch.float64, device=dev)
     d_win = torch.empty(total, dtype=torch.uint8, device=dev)
     d_base = torch.empty(total, dtype=torch.float64, device=dev)            # supplied baseline PSNRs: best HEVC intra mode
     h_psnr_all = torch.empty(total, dtype=torch.float64).pin_memory()      # e2e arm: the PSNRs of all sizes land in one pinned array
-    h_gathered = torch.empty(total * world, dtype=torch.float64).pin_memory() if (rank == 0 and world > 1) else None
+    h_gathered = torch.empty(sum(counts), dtype=torch.float64).pin_memory() if (rank == 0 and world > 1) else None
     per_w, off = {}, 0
     for w, is_fc in WIDTHS:
-        idx, rows, cols = offline.blocks_of_images(N_IMAGES, HEIGHT, WIDTH_IMAGE, w)
+        idx, rows, cols = offline.blocks_of_images(n_local, HEIGHT, WIDTH_IMAGE, w)
         n = len(rows)
         per_w[w] = {
             'is_fc': is_fc, 'n': n, 'off': off,
@@ -279,7 +310,7 @@ def main():
     hb0.record()
     for w, _ in WIDTHS:
         p = per_w[w]
-        eng.hevc_best_mode_device(w, d_images.data_ptr(), N_IMAGES, HEIGHT, WIDTH_IMAGE, p['d_idx'].data_ptr(),
+        eng.hevc_best_mode_device(w, d_images.data_ptr(), n_local, HEIGHT, WIDTH_IMAGE, p['d_idx'].data_ptr(),
                                   p['d_rows'].data_ptr(), p['d_cols'].data_ptr(), p['n'], (0, 0), None,
                                   d_base.data_ptr() + 8 * p['off'], None, torch.cuda.current_stream().cuda_stream)
     hb1.record()
@@ -296,14 +327,14 @@ def main():
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            eng.predict_image_blocks_device(w, p['is_fc'], d_images.data_ptr(), N_IMAGES, HEIGHT, WIDTH_IMAGE,
+            eng.predict_image_blocks_device(w, p['is_fc'], d_images.data_ptr(), n_local, HEIGHT, WIDTH_IMAGE,
                                             p['d_idx'].data_ptr(), p['d_rows'].data_ptr(), p['d_cols'].data_ptr(), p['n'],
                                             (0, 0), None, p['d_u8'].data_ptr(), d_psnr.data_ptr() + 8 * p['off'], stream)
             if record:
                 e1.record()
                 size_events[w].append((e0, e1))
         eng.win_flags_device(d_psnr.data_ptr(), d_base.data_ptr(), total, d_win.data_ptr(), stream)
-        return offline.gather_statistics(d_psnr, d_win, rank, world)
+        return offline.gather_statistics(d_psnr, d_win, rank, world, counts=counts if ragged else None)
 
     def step_e2e():
         # smallest block list first: its host-side validation is short, so the GPU starts at once and the validation of
@@ -320,7 +351,7 @@ def main():
         wins = psnr_all > base_host                      # = (psnr - baseline > 0), comparing_pnn_ipfcns_hevc_best_mode.py:87
         if world > 1:
             g_psnr, g_win = offline.gather_statistics(psnr_all.to(dev, non_blocking=True), wins.to(dev, non_blocking=True),
-                                                      rank, world)
+                                                      rank, world, counts=counts if ragged else None)
             if rank == 0:
                 return offline.reduce_statistics_device(g_psnr, g_win, pinned=h_gathered)
             return None
@@ -365,7 +396,7 @@ def main():
     launches = eng.launch_count - launches0
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_per_step = ms_total / args.steps
-    value = world * total / (ms_per_step * 1e-3)
+    value = total_job / (ms_per_step * 1e-3)
 
     # ---- end-to-end arm (host buffers through the C ABI) -----------------------------------------
     for _ in range(0 if args.skip_e2e else 2):
@@ -383,8 +414,10 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    h2d = sum(images_np.nbytes + 12 * per_w[w]['n'] for w, _ in WIDTHS)
-    d2h = sum(per_w[w]['n'] * (w * w + 8) for w, _ in WIDTHS)
+    # whole job, per step: every block size uploads the images and its block list, and reads predictions + PSNRs back
+    n_images_job = sum(len(sd) for sd in seeds_of)
+    h2d = sum(n_images_job * HEIGHT * WIDTH_IMAGE + 12 * blocks[w] for w, _ in WIDTHS)
+    d2h = sum(blocks[w] * (w * w + 8) for w, _ in WIDTHS)
 
     if rank == 0:
         per_size = {}
@@ -399,13 +432,18 @@ def main():
             pass
         peak = peaks.get('bf16_tflops_sustained', 1590.0 if not peaks else None) or 1590.0
         achieved = prof['gemm_flops'] / (prof['gemm_ms'] * 1e-3) / 1e12 if prof['gemm_ms'] > 0 else 0.
+        # DRAM bytes of one launch of the dominant kernel: read from the committed summary of the `ncu --set full` capture
+        # (profiles/roofline_traffic.json, written by tools/ncu_summaries.py), not a literal
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+        except Exception:
+            pass
         roofline = {
             'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 bf16x3 implicit GEMM)', 'achieved': achieved, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': achieved / peak,
-            # DRAM read + write bytes of one launch from the committed `ncu --set full` capture (profiles/): FC-4 hidden layer,
-            # M = 386377 rows, N = K = 1200; its algorithmic bytes (A hi+lo read once + hi/lo output) are 3.709e9
-            'traffic': 3.726e9, 'traffic_launch': 'gemm_tc_kernel M=386377 N=1200 K=1200 (profiles/r1_gemm_tc_full_summary.txt)',
-            'traffic_algorithmic_bytes': 3.709e9,
+            'traffic': traffic.get('dram_bytes_per_launch'), 'traffic_launch': traffic.get('launch'),
+            'traffic_algorithmic_bytes': traffic.get('algorithmic_bytes_per_launch'), 'traffic_source': traffic.get('source'),
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)' if peaks
                            else 'fallback 1.59 PFLOP/s (B200_PROFILING.md)',
             'mma_passes': 3, 'frac_of_tensor_issue': 3. * achieved / peak,
@@ -416,11 +454,11 @@ def main():
         }
         line = {
             'metric': METRIC, 'value': value, 'unit': 'predictions/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': 'bf16x3 (bf16 hi/lo operands, 3 MMA passes, f32 accumulate)'
             if args.precision == 'bf16x3' else 'f32', 'data': 'synthetic', 'config': cfg,
             'per_size': per_size, 'roofline': roofline,
-            'e2e': {'value': world * total / e2e_s, 'unit': 'predictions/s', 'h2d_bytes_per_step': h2d,
+            'e2e': {'value': total_job / e2e_s, 'unit': 'predictions/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': 1e3 * e2e_s,
                     'mean_psnr_pnn': stats['mean_psnr_pnn'], 'frequency_win_pnn': stats['frequency_win_pnn']},
             'gpu_launches': launches, 'clocks': clocks,

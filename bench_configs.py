@@ -1,0 +1,126 @@
+"""Builder-run records of the other BASELINE.json configurations, in bench.py's JSON schema (`python bench.py --config ...`).
+
+  conv64 : configs[2], CONV-64 with seeded random-init weights, batch sweep; `value` at the largest batch, with contexts
+           resident in HBM; roofline = algorithmic FLOPs of the tcgen05 GEMM launches against the measured bf16 peak.
+  hm     : configs[3], HM-16.15 substitution encoder + decoder on the synthetic 1080p frame at QP 32, the reference's codec
+           sources built against libpnn_cuda (hm/build_hm.sh) and, beside it, against the CPU baseline backend
+           (oracle/_ref/libpnn_ref.so); roofline of the in-loop path = parameter bytes / call time against the HBM peak.
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+MEAN = 117.8952234192841
+PARAMS = {4: 2998816, 8: 3344464, 16: 1339073, 32: 5622657, 64: 20652545}
+MACS64 = 1180696576
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def run_conv64(args, emit):
+    import torch
+    from context_adaptive_neural_network_based_prediction_b200 import Engine, weights
+    dev = torch.device('cuda', 0)
+    tmp = tempfile.mkdtemp(prefix='pnn_bench_')
+    path = os.path.join(tmp, 'net_64.pnnw')
+    weights.save_flat(path, 64, False, weights.init_weights(64, False, seed=64))
+    eng = Engine(mean_training=MEAN, device=0)
+    eng.load_net(path)
+    rng = numpy.random.default_rng(0)
+    sweep, stream = {}, torch.cuda.current_stream().cuda_stream
+    peaks = _peaks()
+    peak = peaks.get('bf16_tflops_sustained') or 1590.0
+    for batch in (1, 16, 256, 1024, 4096):
+        ctx = numpy.clip(rng.normal(0., 40., (min(batch, 256), 5 * 64 * 64)), -118., 137.).astype(numpy.float32)
+        reps = -(-batch // ctx.shape[0])
+        above = torch.from_numpy(numpy.tile(ctx[:, :3 * 64 * 64], (reps, 1))[:batch]).to(dev)
+        left = torch.from_numpy(numpy.tile(ctx[:, 3 * 64 * 64:], (reps, 1))[:batch]).to(dev)
+        out = torch.empty((batch, 64 * 64), dtype=torch.float32, device=dev)
+        for _ in range(max(3, args.warmup)):
+            eng.predict_batch_device(64, False, above.data_ptr(), left.data_ptr(), batch, out.data_ptr(), stream)
+        torch.cuda.synchronize()
+        steps = max(3, args.steps) if batch >= 256 else 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if batch == 4096:
+            eng.set_profiling(True)
+            eng.profile_report()
+        e0.record()
+        for _ in range(steps):
+            eng.predict_batch_device(64, False, above.data_ptr(), left.data_ptr(), batch, out.data_ptr(), stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        sweep[str(batch)] = {'ms': ms, 'predictions_per_s': batch / (ms * 1e-3), 'tflops_algorithmic': 2. * MACS64 * batch / (ms * 1e-3) / 1e12}
+    prof = eng.profile_report()
+    eng.set_profiling(False)
+    achieved = prof['gemm_flops'] / (prof['gemm_ms'] * 1e-3) / 1e12 if prof['gemm_ms'] > 0 else 0.
+    last = sweep['4096']
+    emit({
+        'metric': 'PNN predictions/sec, 64x64 convolutional net', 'value': last['predictions_per_s'], 'unit': 'predictions/s', 'n_gpus': 1,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': last['ms'], 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16x3 (bf16 hi/lo operands, 3 MMA passes, f32 accumulate)', 'data': 'synthetic',
+        'config': {'workload': 'configs[2]: CONV-64, seeded random-init weights, contexts N(0, 40^2) clipped to [-118, 137], batch sweep; '
+                               'value at batch 4096 with the contexts resident in HBM', 'batch_sweep': sweep,
+                   'l2': 'activations of a batch >= 256 (>1 GB) exceed the 126 MB L2'},
+        'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+                     'frac': achieved / peak, 'traffic': None, 'mma_passes': 3, 'frac_of_tensor_issue': 3. * achieved / peak},
+        'gpu_launches': eng.launch_count,
+    })
+    eng.close()
+
+
+def _run_hm(backend, qp, extra=()):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, 'hm', 'run_hm.py'), '--backend', backend, '--qps', str(qp)] + list(extra),
+                       capture_output=True, text=True)
+    rows = [json.loads(l) for l in p.stdout.splitlines() if l.startswith('{')]
+    if not rows or 'error' in rows[0]:
+        raise RuntimeError('hm/run_hm.py --backend %s failed: %s %s' % (backend, p.stdout[-400:], p.stderr[-400:]))
+    return rows[0]
+
+
+def run_hm(args, emit):
+    peaks = _peaks()
+    qp = 32
+    gpu = _run_hm('direct', qp)
+    cpu = _run_hm('cpu', qp, ['--ref-threads', '8,16'])
+    calls = {}
+    for line in gpu['pnn_encoder']:
+        if line.startswith('pnn_calls width'):
+            parts = line.replace(',', '').split()
+            calls[int(parts[2][:-1])] = (int(parts[3]), float(parts[5]))
+    # in-loop roofline: parameter bytes / call time of the most frequent call (FC-4) against HBM
+    n4, s4 = calls.get(4, (0, 0.))
+    us4 = 1e6 * s4 / max(1, n4)
+    gbs = PARAMS[4] * 4 / (us4 * 1e-6) / 1e9 if us4 > 0 else 0.
+    peak = peaks.get('hbm_gbs') or 6452.8
+    emit({
+        'metric': 'HM-16.15 substitution intra encode, seconds per 1080p frame (wall)', 'value': gpu['encoder_wall_s'], 'unit': 's/frame',
+        'n_gpus': 1, 'steps': 1, 'warmup': 0, 'ms_per_step': 1e3 * gpu['encoder_wall_s'], 'higher_is_better': False, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32 (in-loop FC nets) / bf16x3 (in-loop convolutional nets)', 'data': 'synthetic',
+        'config': {'workload': 'configs[3]: HM-16.15 substitution encoder + decoder, first-frame intra of the synthetic 1920x1080 4:0:0 frame, '
+                               'QP %d, intra_main_rext.cfg, seeded random-init nets, direct binding (hm/direct)' % qp,
+                   'encoder_total_time_s': gpu['encoder_total_time_s'], 'decoder_wall_s': gpu['decoder_wall_s'],
+                   'decoder_hash_ok': gpu['decoder_hash_ok'], 'recon_enc_equals_dec': gpu['recon_enc_equals_dec'], 'bytes': gpu['bytes'],
+                   'pnn_encoder': gpu['pnn_encoder']},
+        'roofline': {'bound': 'hbm', 'kernel': 'fci_persist_kernel (FC-4 in-loop call)', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
+                     'frac': gbs / peak, 'traffic': None,
+                     'note': 'parameter bytes (12.0 MB) / wall time of one call through the codec; the weights stay in shared memory, so '
+                             'this is an equivalent bandwidth, bounded by the PCIe doorbell round trips and three all-to-all exchanges'},
+        'cpu_baseline': {'value': cpu['encoder_wall_s'], 'unit': 's/frame', 'cores': cpu['host_cores'], 'kind': 'port',
+                         'sample': 'the same codec objects linked against oracle/_ref/libpnn_ref.so (libtorch-CPU, FC nets 8 threads, '
+                                   'convolutional nets 16 threads: the fastest setting of tools/ref_backend_latency.py), same frame, same QP',
+                         'bytes': cpu['bytes'], 'pnn_encoder': cpu['pnn_encoder'], 'wall_ratio_cpu_over_gpu': cpu['encoder_wall_s'] / gpu['encoder_wall_s']},
+        'e2e': {'value': gpu['encoder_wall_s'], 'unit': 's/frame', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None},
+        'gpu_launches': None,
+    })

@@ -17,7 +17,7 @@ EXPORTS = (
     'pnn_last_hm_device_ms', 'pnn_version', 'pnn_debug_get_activation', 'pnn_win_flags_device', 'pnn_set_profiling',
     'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused', 'pnn_hevc_best_mode', 'pnn_hevc_best_mode_device',
     'pnn_inspect_net_file', 'pnn_predict_image_blocks_async', 'pnn_synchronize',
-    'pnn_set_hm_cache', 'pnn_hm_cache_stats', 'pnn_set_workspace_budget', 'pnn_register_net', 'pnn_set_context_lazy', 'pnn_create_deferred', 'pnn_release_at_exit',
+    'pnn_set_hm_cache', 'pnn_hm_cache_stats', 'pnn_set_workspace_budget', 'pnn_register_net', 'pnn_set_context_lazy', 'pnn_create_deferred', 'pnn_release_at_exit', 'pnn_warm_up',
 )
 
 PRECISION_FP32 = 0
@@ -41,6 +41,8 @@ def load():
     lib.pnn_create.restype = i32
     lib.pnn_create_deferred.argtypes = lib.pnn_create.argtypes
     lib.pnn_create_deferred.restype = i32
+    lib.pnn_warm_up.argtypes = [vp]
+    lib.pnn_warm_up.restype = i32
     lib.pnn_release_at_exit.argtypes = [vp]
     lib.pnn_release_at_exit.restype = i32
     lib.pnn_destroy.argtypes = [vp]

@@ -3,7 +3,11 @@
 #include "pnn_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -92,11 +96,16 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
 };
 
+// Uploads of a net under construction go to g_upload_stream (the handle's load stream), like the kernels that re-tile them:
+// a plain cudaMemcpy from pageable memory may return before its DMA has landed, and is only ordered with the legacy stream.
+// The source vector may die right after the call (the copy out of pageable memory is staged before the call returns).
+thread_local cudaStream_t g_upload_stream = nullptr;
+
 template <typename T>
 T* upload(const std::vector<T>& v, std::vector<std::unique_ptr<DevBuf>>& keep) {
     keep.emplace_back(new DevBuf());
     keep.back()->reserve(std::max<size_t>(v.size() * sizeof(T), 16));
-    CUDA_TRY(cudaMemcpy(keep.back()->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpyAsync(keep.back()->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_upload_stream));
     return (T*)keep.back()->p;
 }
 
@@ -143,6 +152,12 @@ struct Net {
     DevBuf hm_vec[3];
     const float* fci_images = nullptr;
     int fci_stride = 0;
+    struct TileJob {
+        const float* w;
+        int K, N;
+        uint8_t* tiles;
+    };
+    std::vector<TileJob> tile_jobs;           // tcgen05 weight tiles still to be made (ensure_tiles)
     // memo of in-loop results keyed by the exact staged context (direct-mapped; pnn_set_hm_cache)
     struct HmCache {
         size_t entries = 0, key_words = 0, out_words = 0;
@@ -258,11 +273,13 @@ int add_buf(Net& net, int64_t elems, bool fp32_only = false) {
 
 void add_gemm_weights(Net& net, Step& st, const std::vector<float>& w_kn, const std::vector<float>& bias) {
     st.d_w32 = upload(w_kn, net.dev);
-    // [K][N] fp32 -> pre-swizzled bf16 hi/lo tiles, on the device (34 M weights on one host thread cost seconds of start-up)
+    // [K][N] fp32 -> pre-swizzled bf16 hi/lo tiles: made on the device (34 M weights on one host thread cost seconds of
+    // start-up) by the first call that runs the tensor-core kernels of this net (ensure_tiles), never while loading: the
+    // persistent kernel of the in-loop path may hold every SM at that moment
     net.dev.emplace_back(new DevBuf());
     net.dev.back()->reserve(tc_total_bytes(st.g.N, st.g.K));
-    launch_make_tc_tiles(st.d_w32, st.g.K, st.g.N, (uint8_t*)net.dev.back()->p, nullptr);
     st.d_wt = (const uint8_t*)net.dev.back()->p;
+    net.tile_jobs.push_back({st.d_w32, st.g.K, st.g.N, (uint8_t*)net.dev.back()->p});
     st.d_bias = upload(bias, net.dev);
 }
 
@@ -561,6 +578,15 @@ struct pnn_handle {
     int32_t* hm_staged = nullptr;    // page-aligned inside hm_staged_storage, pinned (cudaHostRegister) once the device is up: header + 5*64*64 ints
     std::vector<int32_t> hm_staged_storage;
     bool device_ready = false;
+    // warm-up thread (pnn_warm_up): device initialisation and the upload of the registered nets run beside the caller
+    std::thread bg;
+    std::mutex mu;                            // nets / pending / loading_key while the warm-up thread is alive
+    std::condition_variable cv;
+    std::atomic<bool> bg_active{false}, bg_init_done{false}, persist_stale{false};
+    bool bg_started = false;
+    std::string bg_error;
+    std::pair<int, int> loading_key{0, -1};   // the net the warm-up thread is uploading right now
+    cudaStream_t stream_load = nullptr;
     int32_t* hm_out = nullptr;       // pinned, 64*64 ints
     int32_t* d_hm_out_mapped = nullptr;      // device alias of hm_out (mapped pinned memory)
     float* hm_out_raw = nullptr;             // pinned + mapped, 64*64 floats (raw prediction)
@@ -617,14 +643,28 @@ static inline void req_store(volatile uint64_t* p, uint32_t payload, unsigned se
     __atomic_store_n((uint64_t*)p, (uint64_t)payload | ((uint64_t)seq << 32), __ATOMIC_RELEASE);
 }
 
-// Asks the persistent FC kernel to exit.  Everything enqueued afterwards (any stream) runs once its CTAs have left the SMs;
-// the host does not wait.  Called at the top of every entry point that needs the GPU for something else.
-static void persist_stop(pnn_handle* h) {
+// The persistent FC kernel takes every SM (one CTA of ~200 KB shared memory each): a second one, or any other kernel of this
+// process, would queue behind it for ever.  So at most ONE handle of the process owns a running persistent kernel, and any
+// handle that is about to use the GPU for something else first asks the owner's kernel to leave.
+static std::mutex g_persist_mu;
+static pnn_handle* g_persist_owner = nullptr;
+
+static void persist_stop_locked(pnn_handle* h) {
     if (!h->persist_running) return;
     h->fc_seq = next_seq(h->fc_seq);
     req_store(h->fci_req + 0, FCI_CMD_QUIT, h->fc_seq);
     h->persist_running = false;
     h->fc_calls_since_stop = 0;
+    if (g_persist_owner == h) g_persist_owner = nullptr;
+}
+
+// Asks the persistent FC kernel (of this handle, and of any other handle of the process) to exit.  Everything enqueued
+// afterwards (any stream) runs once its CTAs have left the SMs; the host does not wait.  Called at the top of every entry
+// point that needs the GPU for something else.
+static void persist_stop(pnn_handle* h) {
+    std::lock_guard<std::mutex> lock(g_persist_mu);
+    if (g_persist_owner && g_persist_owner != h) persist_stop_locked(g_persist_owner);
+    persist_stop_locked(h);
 }
 
 static void drop_hm_caches(pnn_handle* h) {
@@ -667,16 +707,27 @@ struct ProfScope {
     }
 };
 
-void load_flat_file(pnn_handle* h, const FlatFile& ff);
+void load_flat_file(pnn_handle* h, const FlatFile& ff, bool from_warm_up = false);
 
 Net* find_net(pnn_handle* h, int width, int is_fc) {
-    auto it = h->nets.find({width, is_fc ? 1 : 0});
+    const std::pair<int, int> key{width, is_fc ? 1 : 0};
+    std::unique_lock<std::mutex> lock(h->mu, std::defer_lock);
+    if (h->bg_active.load()) lock.lock();
+    auto it = h->nets.find(key);
     if (it == h->nets.end()) {
-        auto pend = h->pending.find({width, is_fc ? 1 : 0});
+        if (lock.owns_lock() && h->loading_key == key) {
+            // the warm-up thread is uploading exactly this net
+            h->cv.wait(lock, [&] { return h->loading_key != key; });
+            it = h->nets.find(key);
+        }
+    }
+    if (it == h->nets.end()) {
+        auto pend = h->pending.find(key);
         if (pend != h->pending.end()) {
             // registered earlier, needed now
             const pnn_handle::Pending p = pend->second;
             h->pending.erase(pend);
+            if (lock.owns_lock()) lock.unlock();
             Trace trace("load at first use");
             FlatFile ff;
             {
@@ -684,7 +735,8 @@ Net* find_net(pnn_handle* h, int width, int is_fc) {
                 if (!p.graph) ff = read_flat(p.path);
             }
             load_flat_file(h, p.graph ? *p.graph : ff);
-            it = h->nets.find({width, is_fc ? 1 : 0});
+            if (h->bg_active.load()) lock.lock();
+            it = h->nets.find(key);
         }
     }
     if (it == h->nets.end()) {
@@ -733,6 +785,15 @@ Act act_of(Net& net, int buf) {
     a.p0 = net.ws0[buf]->p;
     a.p1 = net.ws1[buf]->p;
     return a;
+}
+
+// Makes the tcgen05 weight tiles of `net` on `stream`, ahead of the first launches that read them (same stream: ordered).
+// The caller has asked the persistent kernel to leave.
+void ensure_tiles(pnn_handle* h, Net& net, cudaStream_t stream) {
+    if (net.tile_jobs.empty() || h->precision != PNN_PRECISION_BF16X3) return;
+    for (const Net::TileJob& job : net.tile_jobs) h->launches += launch_make_tc_tiles(job.w, job.K, job.N, job.tiles, stream);
+    net.tile_jobs.clear();
+    CUDA_TRY(cudaGetLastError());
 }
 
 // Runs every layer of `net` on `n` samples whose contexts are already in the input buffers.
@@ -861,6 +922,7 @@ void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int H
     const bool split = h->precision == PNN_PRECISION_BF16X3;
     const int64_t cap = choose_capacity(h, net, n);
     ensure_workspace(net, cap);
+    ensure_tiles(h, net, stream);
     for (int64_t s0 = 0; s0 < n; s0 += cap) {
         const int64_t m = std::min(cap, n - s0);
         GatherLaunch G{};
@@ -915,6 +977,7 @@ void batch_device(pnn_handle* h, Net& net, const float* d_a, const float* d_l, i
     const bool split = h->precision == PNN_PRECISION_BF16X3;
     const int64_t cap = choose_capacity(h, net, n);
     ensure_workspace(net, cap);
+    ensure_tiles(h, net, stream);
     for (int64_t s0 = 0; s0 < n; s0 += cap) {
         const int64_t m = std::min(cap, n - s0);
         if (net.is_fc) {
@@ -938,20 +1001,30 @@ int fail(pnn_handle* h, const std::exception& e) {
     return -1;
 }
 
-void load_flat_file(pnn_handle* h, const FlatFile& ff) {
+void load_flat_file(pnn_handle* h, const FlatFile& ff, bool from_warm_up) {
     Trace trace(ff.is_fc ? "  upload + tile (FC net)" : "  upload + tile (conv net)");
-    persist_stop(h);                          // the persistent kernel holds pointers into the nets
+    // the persistent kernel holds pointers into the nets it serves: the caller's thread stops it here, the warm-up thread
+    // only leaves a note (it must not touch the doorbell the caller may be ringing)
+    if (!from_warm_up) persist_stop(h);
     std::unique_ptr<Net> net(new Net());
     net->W = ff.width;
     net->is_fc = ff.is_fc;
+    g_upload_stream = h->stream_load;
     if (ff.width != 4 && ff.width != 8 && ff.width != 16 && ff.width != 32 && ff.width != 64) {
         throw std::runtime_error("unsupported target width " + std::to_string(ff.width));
     }
     if (ff.is_fc) build_fc(*net, ff);
     else build_conv(*net, ff);
-    CUDA_TRY(cudaDeviceSynchronize());        // the tiling kernels read host-pageable uploads that are already complete; surface errors here
-    h->pending.erase({ff.width, ff.is_fc ? 1 : 0});
-    h->nets[{ff.width, ff.is_fc ? 1 : 0}] = std::move(net);
+    // (not cudaDeviceSynchronize: the persistent kernel of the in-loop path may be running and never finishes by itself)
+    CUDA_TRY(cudaStreamSynchronize(h->stream_load));
+    CUDA_TRY(cudaGetLastError());
+    {
+        std::unique_lock<std::mutex> lock(h->mu, std::defer_lock);
+        if (h->bg_active.load()) lock.lock();
+        h->pending.erase({ff.width, ff.is_fc ? 1 : 0});
+        h->nets[{ff.width, ff.is_fc ? 1 : 0}] = std::move(net);
+    }
+    if (from_warm_up && ff.is_fc && ff.width <= 8) h->persist_stale.store(true);
 }
 
 void load_net_impl(pnn_handle* h, const std::string& path) { load_flat_file(h, read_flat(path)); }
@@ -1006,6 +1079,7 @@ static void init_device(pnn_handle* h) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream_load, cudaStreamNonBlocking));
     for (auto& set : h->in_set) {
         CUDA_TRY(cudaEventCreateWithFlags(&set.uploaded, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&set.consumed, cudaEventDisableTiming));
@@ -1030,8 +1104,61 @@ static void init_device(pnn_handle* h) {
 }
 
 static void ensure_device(pnn_handle* h) {
-    if (!h->device_ready) init_device(h);
+    if (h->bg_started) {
+        // pnn_warm_up is initialising the device on its own thread
+        while (!h->bg_init_done.load()) std::this_thread::sleep_for(std::chrono::microseconds(50));
+        if (!h->bg_error.empty()) throw std::runtime_error(h->bg_error);
+    } else if (!h->device_ready) {
+        init_device(h);
+    }
     CUDA_TRY(cudaSetDevice(h->device));
+}
+
+// Body of the warm-up thread: device initialisation, then the registered nets in the order the codec first needs them.
+static void warm_up_thread(pnn_handle* h) {
+    try {
+        init_device(h);
+    } catch (const std::exception& e) {
+        h->bg_error = e.what();
+    }
+    h->bg_init_done.store(true);
+    if (h->bg_error.empty()) {
+        for (;;) {
+            pnn_handle::Pending p;
+            std::pair<int, int> key;
+            {
+                std::lock_guard<std::mutex> lock(h->mu);
+                if (h->pending.empty()) break;
+                key = h->pending.begin()->first;        // (4,1), (8,1), (16,0), (32,0), (64,0)
+                p = h->pending.begin()->second;
+                h->pending.erase(h->pending.begin());
+                h->loading_key = key;
+            }
+            try {
+                Trace trace("warm-up load");
+                FlatFile ff;
+                if (!p.graph) ff = read_flat(p.path);
+                load_flat_file(h, p.graph ? *p.graph : ff, /*from_warm_up=*/true);
+            } catch (const std::exception& e) {
+                // leave it to the caller's thread, which reports the error of its own attempt
+                std::lock_guard<std::mutex> lock(h->mu);
+                h->pending[key] = p;
+                h->loading_key = {0, -1};
+                h->cv.notify_all();
+                break;
+            }
+            {
+                std::lock_guard<std::mutex> lock(h->mu);
+                h->loading_key = {0, -1};
+            }
+            h->cv.notify_all();
+        }
+    }
+    h->bg_active.store(false);
+}
+
+static void join_warm_up(pnn_handle* h) {
+    if (h->bg.joinable()) h->bg.join();
 }
 
 static int create_impl(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out, bool deferred) {
@@ -1102,8 +1229,18 @@ int pnn_create_deferred(const char* paths_file, float mean_training, int qp_sele
     return create_impl(paths_file, mean_training, qp_selection, device, out, true);
 }
 
+int pnn_warm_up(pnn_handle* h) {
+    if (!h) return -1;
+    if (h->device_ready || h->bg_started) return 0;        // nothing left to overlap
+    h->bg_started = true;
+    h->bg_active.store(true);
+    h->bg = std::thread(warm_up_thread, h);
+    return 0;
+}
+
 int pnn_release_at_exit(pnn_handle* h) {
     if (!h) return -1;
+    join_warm_up(h);
     if (!h->device_ready) return 0;
     Trace trace("pnn_release_at_exit");
     cudaSetDevice(h->device);
@@ -1140,6 +1277,7 @@ int pnn_inspect_net_file(const char* path, int* width_target, int* is_fully_conn
 
 void pnn_destroy(pnn_handle* h) {
     if (!h) return;
+    join_warm_up(h);
     if (!h->device_ready) {                   // created deferred and never used, or the device initialisation failed early
         delete h;
         return;
@@ -1165,6 +1303,7 @@ void pnn_destroy(pnn_handle* h) {
     }
     if (h->stream_in) cudaStreamDestroy(h->stream_in);
     if (h->stream_out) cudaStreamDestroy(h->stream_out);
+    if (h->stream_load) cudaStreamDestroy(h->stream_load);
     for (auto& set : h->in_set) {
         if (set.uploaded) cudaEventDestroy(set.uploaded);
         if (set.consumed) cudaEventDestroy(set.consumed);
@@ -1541,6 +1680,8 @@ static bool persist_start(pnn_handle* h) {
     if (h->persist_running) return true;
     if (!persist_wanted(h)) return false;
     FciPersist P{};
+    std::unique_lock<std::mutex> lock(h->mu, std::defer_lock);
+    if (h->bg_active.load()) lock.lock();
     for (int i = 0; i < 2; ++i) {
         auto it = h->nets.find({4 << i, 1});
         if (it == h->nets.end() || !it->second->fci_images) continue;
@@ -1552,6 +1693,7 @@ static bool persist_start(pnn_handle* h) {
         n.present = 1;
         n.stride = it->second->fci_stride;
     }
+    if (lock.owns_lock()) lock.unlock();
     if (!P.net[0].present && !P.net[1].present) return false;
     if (!h->fci_req) {
         CUDA_TRY(cudaHostAlloc((void**)&h->fci_req, FCI_REQ_PAIRS * sizeof(uint2), cudaHostAllocMapped));
@@ -1580,7 +1722,13 @@ static bool persist_start(pnn_handle* h) {
         }
         P.stamps = (unsigned long long*)h->d_fc_stamps.p;
     }
-    const cudaError_t e = launch_fci_persist(P, h->stream);
+    cudaError_t e;
+    {
+        std::lock_guard<std::mutex> owner_lock(g_persist_mu);
+        if (g_persist_owner && g_persist_owner != h) persist_stop_locked(g_persist_owner);   // its kernel leaves, ours queues behind
+        e = launch_fci_persist(P, h->stream);
+        if (e == cudaSuccess) g_persist_owner = h;
+    }
     if (e != cudaSuccess) {
         // 148 CTAs of ~200 KB cannot be co-resident on this device / partition: serve the calls layer by layer instead
         cudaGetLastError();
@@ -1673,6 +1821,7 @@ static void run_hm_fc_persist(pnn_handle* h, Net& net) {
     req_store(req + 0, cmd, seq);
     h->fc_calls_since_stop += 1;
     long long spins = 0;
+    bool warned = false;
     const std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
     for (int n = 0; n < n_out; ++n) {
         for (;;) {
@@ -1683,13 +1832,20 @@ static void run_hm_fc_persist(pnn_handle* h, Net& net) {
                 h->hm_out[n] = (int32_t)(uint32_t)b;
                 break;
             }
-            if ((++spins & 0xfffff) == 0 &&
+            if ((++spins & 0xfffff) == 0 && Trace::on() && !warned &&
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 1.) {
+                warned = true;
+                fprintf(stderr, "[pnn timing] waiting > 1 s for the persistent kernel: W=%d seq=%u output %d of %d, stream: %s\n", W, seq, n, n_out,
+                        cudaGetErrorString(cudaStreamQuery(h->stream)));
+            }
+            if ((spins & 0xfffff) == 0 &&
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() > 10.) {
-                // never seen in practice; leave the kernel a way out and report
+                // the kernel never got the SMs (another process or handle holds them) or died: leave it a way out, fall back
+                // to plain launches from now on, and report -- without blocking on the stream
                 persist_stop(h);
                 h->persist_failed = true;
-                const cudaError_t e = cudaStreamSynchronize(h->stream);
-                throw std::runtime_error(std::string("the persistent FC kernel did not answer (") + cudaGetErrorString(e) + ")");
+                throw std::runtime_error(std::string("the persistent FC kernel did not answer within 10 s (") +
+                                         cudaGetErrorString(cudaStreamQuery(h->stream)) + ")");
             }
         }
     }
@@ -1772,6 +1928,7 @@ static void run_hm_graph(pnn_handle* h, Net& net) {
     persist_stop(h);
     ensure_workspace(net, 1);
     cudaStream_t s = h->stream;
+    if (!(net.is_fc && net.fci_images)) ensure_tiles(h, net, s);   // (not under the capture below: made once, not per replay)
     if (!net.hm_exec || net.hm_exec_precision != h->precision) {
         // capture the launch sequence once; every later call replays it (the per-call availability
         // masks travel in the staged header, so no kernel parameter changes between calls)
@@ -1832,6 +1989,7 @@ static uint64_t hash_words(const int32_t* p, size_t n) {
 }
 
 static void run_hm(pnn_handle* h, Net& net) {
+    if (h->persist_stale.exchange(false)) persist_stop(h);    // the warm-up thread added an FC net: relaunch with it
     const int W = net.W;
     const size_t key_words = (size_t)HM_HEADER_INTS + 5 * W * W, out_words = (size_t)2 * W * W;
     Net::HmCache& c = net.cache;
@@ -1871,7 +2029,12 @@ static void run_hm(pnn_handle* h, Net& net) {
 // the net that serves in-loop calls of this width: fully-connected if one is loaded (the reference's choice for widths 4
 // and 8, TComPrediction.cpp:564-566), else convolutional -- a convolutional net may also serve widths 4 and 8
 static Net& hm_net(pnn_handle* h, int width) {
-    const bool has_fc = h->nets.count({width, 1}) != 0 || h->pending.count({width, 1}) != 0;
+    bool has_fc;
+    {
+        std::unique_lock<std::mutex> lock(h->mu, std::defer_lock);
+        if (h->bg_active.load()) lock.lock();
+        has_fc = h->nets.count({width, 1}) != 0 || h->pending.count({width, 1}) != 0 || h->loading_key == std::make_pair(width, 1);
+    }
     return *find_net(h, width, has_fc ? 1 : 0);
 }
 

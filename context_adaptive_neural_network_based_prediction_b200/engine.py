@@ -44,6 +44,10 @@ class Engine(object):
         if create(path, ctypes.c_float(self.mean_training), int(qp_selection), int(device), ctypes.byref(self._h)) != 0:
             raise PnnError(self._lib.pnn_last_error(None).decode())
 
+    def warm_up(self):
+        """After `deferred=True`: device initialisation and net uploads start on a thread of the library (pnn_warm_up)."""
+        self._check(self._lib.pnn_warm_up(self._h))
+
     def close(self):
         if getattr(self, '_h', None) and self._h.value:
             self._lib.pnn_destroy(self._h)

@@ -51,17 +51,23 @@ def evaluate_blocks(engine, images_uint8, width_target, is_fully_connected, rows
     }
 
 
-def gather_statistics(psnrs_local, wins_local, rank, world_size, group=None):
+def gather_statistics(psnrs_local, wins_local, rank, world_size, group=None, counts=None):
     """ONE gather of the per-block statistics to rank 0.
 
-    `psnrs_local` float64 and `wins_local` uint8 are torch tensors (CUDA for NCCL, CPU for gloo) of the same
-    length on every rank.  They are packed into one float64 message (win flags are exactly representable),
-    so a single collective is issued.  Returns (psnrs [world, n], wins [world, n]) on rank 0, (None, None)
-    elsewhere.
+    `psnrs_local` float64 and `wins_local` uint8 are torch tensors (CUDA for NCCL, CPU for gloo).  They travel as bytes in
+    one message of 9 bytes per block (8 of the float64 PSNR, 1 of the win flag), so a single collective is issued and both
+    arrive bit-exactly.  `counts` (blocks per rank) allows ranks to hold different numbers of blocks, as happens when 100
+    images are sharded over 8 ranks: messages are padded to the largest count and cut back on rank 0.
+    Returns (psnrs, wins) on rank 0 -- tensors [world, n] when every rank holds n blocks, else lists of per-rank tensors --
+    and (None, None) elsewhere.
     """
     import torch
     import torch.distributed as dist
-    packed = torch.cat([psnrs_local.to(torch.float64), wins_local.to(torch.float64)])
+    n = psnrs_local.numel()
+    n_max = n if counts is None else max(counts)
+    packed = torch.zeros(9 * n_max, dtype=torch.uint8, device=psnrs_local.device)
+    packed[:8 * n] = psnrs_local.to(torch.float64).contiguous().view(torch.uint8)
+    packed[8 * n_max:8 * n_max + n] = wins_local.to(torch.uint8)
     if world_size == 1:
         out = [packed]
     else:
@@ -69,9 +75,12 @@ def gather_statistics(psnrs_local, wins_local, rank, world_size, group=None):
         dist.gather(packed, out, dst=0, group=group)
     if rank != 0:
         return None, None
-    n = psnrs_local.numel()
-    stacked = torch.stack(out)
-    return stacked[:, :n], stacked[:, n:].to(torch.uint8)
+    sizes = [n] * world_size if counts is None else list(counts)
+    psnrs = [o[:8 * c].view(torch.float64) for o, c in zip(out, sizes)]
+    wins = [o[8 * n_max:8 * n_max + c] for o, c in zip(out, sizes)]
+    if counts is None:
+        return torch.stack(psnrs), torch.stack(wins)
+    return psnrs, wins
 
 
 def reduce_statistics_device(psnrs, wins, pinned=None):
@@ -79,6 +88,8 @@ def reduce_statistics_device(psnrs, wins, pinned=None):
     reduced on the device, the per-block PSNRs come back through one copy (into `pinned`, a pinned float64 tensor of the
     same number of elements, when given)."""
     import torch
+    if isinstance(psnrs, (list, tuple)):                     # ranks with different block counts
+        psnrs, wins = torch.cat(list(psnrs)), torch.cat(list(wins))
     flat = psnrs.reshape(-1)
     mean = flat.mean() if flat.numel() else torch.tensor(float('nan'))
     won = (wins.reshape(-1) != 0).sum()

@@ -1,5 +1,7 @@
 #include "pnn_hm_direct.h"
 
+#include <errno.h>    // program_invocation_short_name (glibc)
+
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -84,6 +86,11 @@ pnn_handle* create(const std::string& path_to_file_paths_to_graphs_output, float
     // HM does not touch the reconstruction between initIntraPatternChType and predIntraAng: the context is copied only
     // when the neural-network mode is actually evaluated
     pnn_set_context_lazy(g_handle, 1);
+    // An encoder will need every net, but not before it has coded its first row of coding tree units (no causal context
+    // there): device initialisation and uploads start now, on a thread of the library.  A decoder may never need them.
+    const char* warm = getenv("PNN_HM_WARM_UP");
+    const bool is_encoder(program_invocation_short_name && strstr(program_invocation_short_name, "Encoder") != NULL);
+    if (warm ? atoi(warm) != 0 : is_encoder) pnn_warm_up(g_handle);
     atexit(print_stats);
     return g_handle;
 }

@@ -80,12 +80,10 @@ for qp in [int(q) for q in args.qps.split(',')]:
     cmd = [enc, '-c', cfg, '-i', yuv, '-b', bit, '-o', rec_e, '-wdt', str(args.width), '-hgt', str(args.height),
            '--InputBitDepth=8', '--InputChromaFormat=400', '--FramesToBeEncoded=1', '--QP=%d' % qp] + extra
     t0 = time.time()
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=None if os.environ.get('PNN_TIMING') else subprocess.PIPE, text=True, env=env)
     t_enc = time.time() - t0
-    if os.environ.get('PNN_TIMING'):
-        sys.stderr.write('--- encoder\n' + p.stderr)
     if p.returncode != 0:
-        print(json.dumps({'qp': qp, 'error': 'encoder failed', 'stderr': p.stderr[-800:], 'stdout': p.stdout[-400:]}))
+        print(json.dumps({'qp': qp, 'error': 'encoder failed', 'stderr': (p.stderr or '')[-800:], 'stdout': p.stdout[-400:]}))
         continue
     enc_total = re.findall(r'Total Time:\s+([0-9.]+) sec', p.stdout)
     bits = re.findall(r'Bytes written to file:\s+(\d+)', p.stdout)
@@ -93,11 +91,9 @@ for qp in [int(q) for q in args.qps.split(',')]:
     enc_stats = open(stats).read().strip().split('\n') if os.path.exists(stats) else []
     stats_d = os.path.join(tmp, 'stats_dec_%d.txt' % qp)
     t0 = time.time()
-    d = subprocess.run([dec, '-b', bit, '-o', rec_d, '-d', '8'] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+    d = subprocess.run([dec, '-b', bit, '-o', rec_d, '-d', '8'] + extra, stdout=subprocess.PIPE, stderr=None if os.environ.get('PNN_TIMING') else subprocess.PIPE, text=True,
                        env=dict(os.environ, PNN_HM_STATS=stats_d))
     t_dec = time.time() - t0
-    if os.environ.get('PNN_TIMING'):
-        sys.stderr.write('--- decoder\n' + d.stderr)
     dec_total = re.findall(r'Total Time:\s+([0-9.]+) sec', d.stdout)
     same = os.path.exists(rec_e) and os.path.exists(rec_d) and open(rec_e, 'rb').read() == open(rec_d, 'rb').read()
     print(json.dumps({

@@ -4,8 +4,11 @@
 
 #include "pnn_cuda.h"
 
+#include <errno.h>    // program_invocation_short_name (glibc)
+
 #include <chrono>
 #include <cmath>
+#include <cstring>
 #include <cstdint>
 #include <fstream>
 
@@ -150,6 +153,11 @@ tensorflow::Status load_graphs(const std::vector<std::string>& vector_paths_to_g
         const tensorflow::Status status(load_graph(vector_paths_to_graphs_output[i], vector_unique_ptrs_session[i]));
         if (!status.ok()) return status;
     }
+    // An encoder will need every net, but not before it has coded its first row of coding tree units (no causal context
+    // there): device initialisation and uploads start now, on a thread of the library.  A decoder may never need them.
+    const char* warm = getenv("PNN_HM_WARM_UP");
+    const bool is_encoder(program_invocation_short_name && strstr(program_invocation_short_name, "Encoder") != NULL);
+    if (g_handle && (warm ? atoi(warm) != 0 : is_encoder)) pnn_warm_up(g_handle);
     return tensorflow::Status::OK();
 }
 

@@ -57,6 +57,13 @@ int pnn_create(const char* paths_file, float mean_training, int qp_selection, in
  */
 int pnn_create_deferred(const char* paths_file, float mean_training, int qp_selection, int device, pnn_handle** out);
 
+/*
+ * After pnn_create_deferred: starts the device initialisation and the upload of the registered nets on a thread of the
+ * library, so that they overlap the caller's own start-up (an encoder works through its first row of coding tree units,
+ * whose blocks have no causal context, before it asks for the first prediction).  Calls that need the device wait for it.
+ */
+int pnn_warm_up(pnn_handle* h);
+
 /* Replaces std::unique_ptr<tensorflow::Session> teardown. */
 void pnn_destroy(pnn_handle* h);
 

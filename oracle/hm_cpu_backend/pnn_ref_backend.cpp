@@ -253,6 +253,7 @@ int pnn_create_deferred(const char* paths_file, float mean, int qp_selection, in
 }
 
 int pnn_release_at_exit(pnn_handle*) { return 0; }
+int pnn_warm_up(pnn_handle*) { return 0; }
 
 const char* pnn_last_error(pnn_handle* h) { return h ? h->error.c_str() : g_error.c_str(); }
 

@@ -156,7 +156,7 @@ def forward(weights, width, is_fc, inputs):
 # slow literal loop versions (validation of the fast path on tiny cases only)
 # ----------------------------------------------------------------------------
 
-def conv2d_same_loops(x, w, b, s):
+def conv2d_same_loops(x, w, b, s, out_dtype=numpy.float32):
     bsz, h, wd, cin = x.shape
     k, _, _, cout = w.shape
     ho, pt, _ = same_padding(h, k, s)
@@ -173,10 +173,10 @@ def conv2d_same_loops(x, w, b, s):
                     if ix < 0 or ix >= wd:
                         continue
                     y[:, oy, ox, :] += x[:, iy, ix, :].astype(numpy.float64) @ w[ky, kx].astype(numpy.float64)
-    return (y + b).astype(numpy.float32)
+    return (y + b).astype(out_dtype)
 
 
-def tconv2d_same_loops(x, w, b, s):
+def tconv2d_same_loops(x, w, b, s, out_dtype=numpy.float32):
     """Scatter form: every input pixel adds in*W[ky,kx] at y = iy*s + ky - pad_before."""
     bsz, h, wd, cin = x.shape
     k, _, cout, _ = w.shape
@@ -196,16 +196,40 @@ def tconv2d_same_loops(x, w, b, s):
                         continue
                     # w[ky,kx] is [Cout,Cin]
                     y[:, oy, ox, :] += x[:, iy, ix, :].astype(numpy.float64) @ w[ky, kx].astype(numpy.float64).T
-    return (y + b).astype(numpy.float32)
+    return (y + b).astype(out_dtype)
 
 
-def merger_loops(in0, in1, w, b):
+def merger_loops(in0, in1, w, b, out_dtype=numpy.float32):
     bsz, _, _, c = in0.shape
     out = numpy.zeros((bsz, 16, c), dtype=numpy.float64)
     for ch in range(c):
         cat = numpy.concatenate([in0[:, :, :, ch].reshape(bsz, -1), in1[:, :, :, ch].reshape(bsz, -1)], axis=1)
         out[:, :, ch] = cat.astype(numpy.float64) @ w[ch].astype(numpy.float64) + b[ch]
-    return out.reshape(bsz, 4, 4, c).astype(numpy.float32)
+    return out.reshape(bsz, 4, 4, c).astype(out_dtype)
+
+
+def forward_conv_loops_float64(weights, above, left):
+    """The whole convolutional PNN with the literal loop layers above, float64 from end to end: an implementation that
+    shares no code with the torch path (no library convolution, no padding helper), used to make the committed goldens
+    of the two pretrained checkpoints (tests/golden/make_loop_goldens.py)."""
+    width = above.shape[1]
+    strides = STRIDES_BRANCH[width]
+    lrelu = lambda v: numpy.maximum(SLOPE * v, v)
+    outs = []
+    for name, x in (('above', above.astype(numpy.float64)), ('left', left.astype(numpy.float64))):
+        for i, s in enumerate(strides):
+            p = 'convolutional/branch_%s/convolution_%d/' % (name, i)
+            x = lrelu(conv2d_same_loops(x, weights[p + 'weights'], weights[p + 'biases'], s, numpy.float64))
+        outs.append(x)
+    p = 'convolutional/merger/channelwise_fully_connected_merger/'
+    x = lrelu(merger_loops(outs[0], outs[1], weights[p + 'weights'], weights[p + 'biases'], numpy.float64))
+    strides_m = strides[::-1]
+    for i, s in enumerate(strides_m):
+        p = 'convolutional/merger/transpose_convolution_%d/' % i
+        x = tconv2d_same_loops(x, weights[p + 'weights'], weights[p + 'biases'], s, numpy.float64)
+        if i != len(strides_m) - 1:
+            x = lrelu(x)
+    return x
 
 
 # ----------------------------------------------------------------------------

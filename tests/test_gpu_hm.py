@@ -354,3 +354,30 @@ def test_lazy_context_staging_gives_the_same_prediction(engine, weights_dir, wid
     finally:
         engine.set_context_lazy(False)
     numpy.testing.assert_array_equal(eager, lazy)
+
+
+def test_deferred_creation_and_warm_up(weights_dir, tmp_path):
+    """pnn_create_deferred touches no GPU until a call needs it; pnn_warm_up initialises the device and uploads the registered
+    nets on a thread of the library while the caller goes on; predictions equal those of an ordinary handle."""
+    from context_adaptive_neural_network_based_prediction_b200 import Engine
+    paths = {}
+    for width in (4, 8, 16, 32, 64):
+        paths[width], _ = helpers.make_net_file(weights_dir, width, width <= 8, seed=300 + width, gain=helpers.GAIN[(width, width <= 8)])
+    paths_file = str(tmp_path / 'paths.txt')
+    open(paths_file, 'w').write(''.join('%d,0,0,%s\n' % (w, paths[w]) for w in paths))
+    plain = Engine(paths_file=paths_file, qp_selection=22)
+    lazy = Engine(paths_file=paths_file, qp_selection=22, deferred=True)
+    warm = Engine(paths_file=paths_file, qp_selection=22, deferred=True)
+    try:
+        warm.warm_up()
+        for i in range(30):                                   # calls race with the uploads of the warm-up thread
+            width = (4, 8, 16, 4, 8, 32, 4, 64)[i % 8]
+            ctx = _fc_context(width, i)
+            args = (width, ctx) if width <= 8 else (width, ctx[:3 * width * width], ctx[3 * width * width:])
+            want = plain.predict_hm_context(*args)
+            numpy.testing.assert_array_equal(want, lazy.predict_hm_context(*args))
+            numpy.testing.assert_array_equal(want, warm.predict_hm_context(*args))
+    finally:
+        plain.close(); lazy.close(); warm.close()
+    unused = Engine(paths_file=paths_file, qp_selection=22, deferred=True)
+    unused.close()                                            # never touched the device: nothing to tear down

@@ -295,3 +295,23 @@ def test_create_with_paths_file(weights_dir, tmp_path):
         Engine(paths_file=str(tmp_path / 'absent.txt'), qp_selection=22)
     with pytest.raises(PnnError, match='quantization parameter'):
         Engine(paths_file=only_single, qp_selection=0)
+
+
+@pytest.mark.parametrize('width', [4, 8])
+def test_real_checkpoints_against_float64_loop_goldens(engine, golden_dir, width):
+    """The library against goldens that do NOT come from the torch oracle: the literal float64 loop implementation
+    (tests/golden/make_loop_goldens.py) on the two pretrained checkpoints, 240 real-image blocks, outputs up to +-106."""
+    engine.load_net(os.path.join(golden_dir, 'conv%d_single.pnnw' % width))
+    img = numpy.load(os.path.join(golden_dir, 'cliff_luma.npy'))
+    g = numpy.load(os.path.join(golden_dir, 'loop_real.npz'))
+    rows, cols = g['rows_%d' % width], g['cols_%d' % width]
+    for precision in ('bf16x3', 'fp32'):
+        engine.set_precision(precision)
+        for masks in ((0, 0), (4, 4)):
+            out = engine.predict_image_blocks(width, False, img, rows, cols, masks=masks)
+            gold = g['pred_%d_m%d%d' % (width, masks[0], masks[1])]
+            err = float(numpy.abs(out['predictions_float32'] - gold).max())
+            assert err <= TOL[precision], 'max abs error %.3e' % err
+            want_u8 = numpy.clip(numpy.round(numpy.clip(gold.astype(numpy.float32) + numpy.float32(MEAN), 0., 255.)), 0, 255).astype(numpy.uint8)
+            assert (out['predictions_uint8'] == want_u8).mean() >= 0.999
+    engine.set_precision('bf16x3')

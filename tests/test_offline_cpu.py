@@ -46,6 +46,34 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_ragged(rank, world, port, out_dir):
+    """Ranks with different block counts (100 images over 8 ranks: 13 or 12 images each)."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    counts = [41, 29]
+    rng = numpy.random.default_rng(10 + rank)
+    psnrs = torch.from_numpy(rng.uniform(10., 50., counts[rank]))
+    wins = (psnrs > 25.).to(torch.uint8)
+    g_psnr, g_win = offline.gather_statistics(psnrs, wins, rank, world, counts=counts)
+    if rank == 0:
+        stats = offline.reduce_statistics_device(g_psnr, g_win)
+        numpy.save(os.path.join(out_dir, 'ragged.npy'), stats['psnrs_pnn'])
+        numpy.save(os.path.join(out_dir, 'ragged_freq.npy'), numpy.array([stats['frequency_win_pnn']]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_single_gather_with_different_block_counts(tmp_path):
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_ragged, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    want = numpy.concatenate([numpy.random.default_rng(10 + r).uniform(10., 50., c) for r, c in ((0, 41), (1, 29))])
+    numpy.testing.assert_array_equal(numpy.load(str(tmp_path / 'ragged.npy')), want)
+    assert numpy.load(str(tmp_path / 'ragged_freq.npy'))[0] == float((want > 25.).sum()) / want.size
+
+
 def test_single_gather_world_size_2(tmp_path):
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))

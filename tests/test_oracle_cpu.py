@@ -8,6 +8,8 @@ import torch
 
 from oracle import context, epilogue, nets
 
+MEAN = 117.8952234192841
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -299,3 +301,48 @@ def test_golden_real_checkpoints(golden_dir):
             tag = '%d_m%d%d' % (width, masks[0], masks[1])
             numpy.testing.assert_allclose(pred, gold['pred_' + tag], atol=2e-3)
             assert (epilogue.epilogue_numpy(pred, MEAN) == gold['u8_' + tag]).mean() > 0.9995
+
+
+def test_offline_gather_equals_the_reference_numpy_path(golden_dir):
+    """oracle.context.gather_image_blocks against outputs of the reference's OWN sets/common.py
+    (extract_context_portions_targets_from_channels_plus_preprocessing, imported unmodified by
+    tests/golden/make_reference_gather_golden.py): slicing, float32 mean subtraction, masks and FC flattening agree bit
+    for bit, for widths 4 / 8 / 16, four mask pairs, both layouts.  The reference orders its outputs image-major."""
+    import os
+    from oracle import context
+    g = numpy.load(os.path.join(golden_dir, 'reference_gather.npz'))
+    images = g['images']
+    n_img = images.shape[0]
+    for width in (4, 8, 16):
+        rows, cols = g['rows_%d' % width], g['cols_%d' % width]       # first pixel of the above portion = context anchor
+        idx = numpy.repeat(numpy.arange(n_img), len(rows))
+        r, c = numpy.tile(rows, n_img) + width, numpy.tile(cols, n_img) + width
+        for masks in ((0, 0), (4, 0), (0, width), (width, 4)):
+            above, left, flat, targets = context.gather_image_blocks(images, idx, r, c, width, MEAN, masks[0], masks[1])
+            tag = '%d_%d_%d_' % (width, masks[0], masks[1])
+            numpy.testing.assert_array_equal(flat, g['flat_' + tag + 'fc'])
+            numpy.testing.assert_array_equal(above, g['above_' + tag + 'conv'])
+            numpy.testing.assert_array_equal(left, g['left_' + tag + 'conv'])
+            want_targets = targets.astype(numpy.float32)[..., None] - numpy.float32(MEAN)
+            numpy.testing.assert_array_equal(want_targets, g['target_' + tag + 'fc'])
+            numpy.testing.assert_array_equal(want_targets, g['target_' + tag + 'conv'])
+
+
+@pytest.mark.parametrize('width', [4, 8])
+def test_torch_oracle_against_float64_loop_goldens(golden_dir, width):
+    """The torch (oneDNN) oracle against the committed float64 goldens of the literal loop implementation
+    (tests/golden/make_loop_goldens.py) on the two pretrained checkpoints the reference ships, 240 real-image blocks each,
+    outputs spanning +-100 pixel units: two implementations that share no layer code agree to 5e-4."""
+    import os
+    from context_adaptive_neural_network_based_prediction_b200 import weights as W
+    g = numpy.load(os.path.join(golden_dir, 'loop_real.npz'))
+    img = numpy.load(os.path.join(golden_dir, 'cliff_luma.npy'))
+    _, _, wts = W.load_flat(os.path.join(golden_dir, 'conv%d_single.pnnw' % width))
+    rows, cols = g['rows_%d' % width], g['cols_%d' % width]
+    assert len(rows) >= 200
+    for masks in ((0, 0), (4, 4)):
+        above, left, _, _ = context.gather_image_blocks(img[None], numpy.zeros(len(rows), int), rows, cols, width, MEAN, masks[0], masks[1])
+        pred = nets.forward_conv(wts, above, left)[..., 0]
+        gold = g['pred_%d_m%d%d' % (width, masks[0], masks[1])]
+        assert numpy.abs(gold).max() > 50.
+        assert numpy.abs(pred - gold).max() <= 5e-4
