@@ -96,7 +96,121 @@ __global__ void __launch_bounds__(NT) gemm_fp32_kernel(GemmLaunch L) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batch-1 (in-loop) GEMM-shaped layer in fp32: the output map of ONE sample has 16 .. 3072 pixels, far too few rows for the
+// 128-row tensor-core tiles, and the layer is bound by streaming its weights once.  CTA = 16 output pixels x 16 output
+// channels over the WHOLE K (no split-K across CTAs, no partial sums in global memory, no reduce launch).  Thread
+// (ks = t / 16, n = t % 16) accumulates rows k = ks, ks + 16, ... of column n for all 16 pixels: one 4-byte weight load
+// (a warp covers two rows of 64 contiguous bytes) and four 16-byte shared-memory loads of the activation tile
+// a_s[k][16 pixels] (broadcast to the 16 threads of a k) per 16 FMAs.  The 16 k-slices of an output are then added in
+// ascending order.  K is consumed in chunks of SK_CHUNK rows (the implicit-im2col gather of a chunk is staged in shared
+// memory, zero for padding / transposed-convolution borders).  Fixed order, fp32 throughout.
+// ---------------------------------------------------------------------------------------------
+constexpr int SK_CHUNK = 512;
+
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(GemmLaunch L) {
+    __shared__ __align__(16) float a_s[SK_CHUNK][16];             // 32 KB
+    const GemmGeom& g = L.g;
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.x * 16, n0 = blockIdx.y * 16;
+    const int ks = t >> 4, n = t & 15;
+    const float* in = (const float*)L.in.p0;
+    const float* wcol = L.w_fp32 + n0 + n;
+    float acc[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) acc[p] = 0.f;
+    // gather role: thread = (pixel gp = t % 16, 16-byte slot q = t / 16 + 16 j): a slot is four consecutive input channels
+    // of one tap (Cin is a power of two >= 4 in every layer that comes here)
+    const int gp = t & 15, gq0 = t >> 4;
+    const int gm = m0 + gp;
+    const bool g_ok = gm < L.M;
+    int g_oy = 0, g_ox = 0;
+    int64_t g_base = 0;
+    if (g_ok) {
+        const int b = gm / g.P, pp = gm - b * g.P;
+        g_oy = pp / g.OW;
+        g_ox = pp - g_oy * g.OW;
+        g_base = (int64_t)b * g.in_sample_stride;
+    }
+    const int cin_log2 = 31 - __clz(g.Cin);
+    for (int k0 = 0; k0 < g.K; k0 += SK_CHUNK) {
+        const int kc = min(SK_CHUNK, g.K - k0);
+        // every global load of the chunk is requested up front: the thread's 32 weights (rows ks, ks + 16, ...) and its 8
+        // 16-byte pieces of the activation tile; one round trip to L2 per chunk
+        float w[SK_CHUNK / 16];
+#pragma unroll
+        for (int u = 0; u < SK_CHUNK / 16; ++u) w[u] = ks + 16 * u < kc ? __ldg(wcol + (int64_t)(k0 + ks + 16 * u) * g.N) : 0.f;
+        float4 v[SK_CHUNK / 64];
+#pragma unroll
+        for (int j = 0; j < SK_CHUNK / 64; ++j) {
+            const int kk = 4 * (gq0 + 16 * j);
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kk < kc && g_ok) {
+                const int k = k0 + kk;
+                const int tap = k >> cin_log2, ci = k & (g.Cin - 1);
+                const int tyy = tap / g.TW, txx = tap - tyy * g.TW;
+                const int iy = g_oy * g.sy_o + tyy * g.sy_t + g.cy;
+                const int ix = g_ox * g.sx_o + txx * g.sx_t + g.cx;
+                if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
+                    v[j] = __ldg(reinterpret_cast<const float4*>(in + g_base + (((int64_t)iy * g.IW + ix) << cin_log2) + ci));
+                }
+            }
+        }
+        __syncthreads();                                          // the previous chunk has been consumed
+#pragma unroll
+        for (int j = 0; j < SK_CHUNK / 64; ++j) {
+            const int kk = 4 * (gq0 + 16 * j);
+            if (kk < kc) {
+                a_s[kk][gp] = v[j].x;
+                a_s[kk + 1][gp] = v[j].y;
+                a_s[kk + 2][gp] = v[j].z;
+                a_s[kk + 3][gp] = v[j].w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < SK_CHUNK / 16; ++u) {
+            const int kk = ks + 16 * u;
+            if (kk < kc) {
+                const float4* row = reinterpret_cast<const float4*>(a_s[kk]);
+                const float4 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+                const float wu = w[u];
+                acc[0] = fmaf(a0.x, wu, acc[0]);   acc[1] = fmaf(a0.y, wu, acc[1]);   acc[2] = fmaf(a0.z, wu, acc[2]);   acc[3] = fmaf(a0.w, wu, acc[3]);
+                acc[4] = fmaf(a1.x, wu, acc[4]);   acc[5] = fmaf(a1.y, wu, acc[5]);   acc[6] = fmaf(a1.z, wu, acc[6]);   acc[7] = fmaf(a1.w, wu, acc[7]);
+                acc[8] = fmaf(a2.x, wu, acc[8]);   acc[9] = fmaf(a2.y, wu, acc[9]);   acc[10] = fmaf(a2.z, wu, acc[10]); acc[11] = fmaf(a2.w, wu, acc[11]);
+                acc[12] = fmaf(a3.x, wu, acc[12]); acc[13] = fmaf(a3.y, wu, acc[13]); acc[14] = fmaf(a3.z, wu, acc[14]); acc[15] = fmaf(a3.w, wu, acc[15]);
+            }
+        }
+    }
+    // the 16 k-slices of every output, added in ascending order: red[ks][pixel][channel] reuses the activation tile
+    __syncthreads();
+    float* red = &a_s[0][0];                                      // 16 * 16 * 16 floats = 16 KB
+#pragma unroll
+    for (int p = 0; p < 16; ++p) red[(ks * 16 + p) * 16 + n] = acc[p];
+    __syncthreads();
+    const int p = t >> 4;                                         // thread = (pixel p, channel n)
+    float sum = 0.f;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) sum += red[(s * 16 + p) * 16 + n];
+    const int m = m0 + p, nn = n0 + n;
+    if (m >= L.M || nn >= g.N) return;
+    float v = sum + L.bias[nn];
+    if (g.leaky) v = leaky_relu(v);
+    const int b = m / g.P, pp = m - b * g.P;
+    const int oy = pp / g.OW, ox = pp - oy * g.OW;
+    const int64_t o = (int64_t)b * g.out_sample_stride + ((int64_t)(oy * g.osy + g.ooy) * g.OWf + (ox * g.osx + g.oox)) * g.N + nn;
+    if (L.out_mode == OUT_FINAL) final_store(L.fin, o, v);
+    else ((float*)L.out.p0)[o] = v;
+}
+
 }  // namespace
+
+int launch_gemm_skinny(const GemmLaunch& L, cudaStream_t stream) {
+    if (L.M == 0) return 0;
+    dim3 grid((L.M + 15) / 16, (L.g.N + 15) / 16);
+    gemm_skinny_kernel<<<grid, 256, 0, stream>>>(L);
+    return 1;
+}
 
 int launch_gemm_fp32(const GemmLaunch& L, cudaStream_t stream) {
     if (L.M == 0) return 0;

@@ -84,7 +84,7 @@ struct HevcLaunch {
     const int32_t* rows;
     const int32_t* cols;
     int64_t n;
-    int H, Wimg, W, mask_w, mask_h;
+    int H, Wimg, W, mask_w, mask_h, n_images;
     uint8_t* best_index;
     double* psnr;
     uint8_t* pred;
@@ -103,8 +103,22 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_best_mode_kernel(HevcLaunch L
     const int W = L.W, shift = 31 - __clz(W), px = W * W;
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
     for (int64_t i = (int64_t)blockIdx.x * WARPS + warp; i < L.n; i += nwarps) {
-        const uint8_t* img = L.images + (int64_t)(L.image_index ? L.image_index[i] : 0) * L.H * L.Wimg;
+        const int img_i = L.image_index ? L.image_index[i] : 0;
         const int r0 = L.rows[i], c0 = L.cols[i];
+        // the device-pointer entry point cannot check its block list on the host: a block (or the first pixel of its intra
+        // pattern) outside the image, or a bad image index, yields best_index 255 / PSNR NaN / a zero prediction instead of
+        // reads out of bounds
+        if (img_i < 0 || img_i >= L.n_images || r0 < 1 || c0 < 1 || r0 + W > L.H || c0 + W > L.Wimg) {
+            if (lane == 0) {
+                if (L.best_index) L.best_index[i] = 255;
+                if (L.psnr) L.psnr[i] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+            if (L.pred) {
+                for (int p = lane; p < px; p += 32) L.pred[i * px + p] = 0;
+            }
+            continue;
+        }
+        const uint8_t* img = L.images + (int64_t)img_i * L.H * L.Wimg;
         const int rr = r0 - 1, cr = c0 - 1;                             // comparing_pnn_ipfcns_hevc_best_mode.py:234-235
         // intraprediction.py:73-88 (pattern size) + extracted_hevc_intraprediction.cpp:34-84 (padding with the last pixel)
         int wp = 2 * W + 1 - L.mask_w, hp = 2 * W + 1 - L.mask_h;
@@ -164,9 +178,9 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_best_mode_kernel(HevcLaunch L
 
 int launch_hevc_best_mode(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols, int64_t n,
                           int H, int Wimg, int W, int mask_w, int mask_h, uint8_t* best_index, double* psnr, uint8_t* pred,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int n_images) {
     if (n == 0) return 0;
-    HevcLaunch L{images, image_index, rows, cols, n, H, Wimg, W, mask_w, mask_h, best_index, psnr, pred};
+    HevcLaunch L{images, image_index, rows, cols, n, H, Wimg, W, mask_w, mask_h, n_images, best_index, psnr, pred};
     int64_t grid = (n + WARPS - 1) / WARPS;
     if (grid > 148 * 16) grid = 148 * 16;
     hevc_best_mode_kernel<<<(unsigned)grid, WARPS * 32, 0, stream>>>(L);

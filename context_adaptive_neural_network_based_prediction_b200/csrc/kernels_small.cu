@@ -24,7 +24,8 @@ __global__ void gather_image_kernel(GatherLaunch L) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; i < L.n; i += (int64_t)gridDim.x * blockDim.y) {
         const int img = L.image_index ? L.image_index[i] : 0;
         const int r0 = L.rows[i], c0 = L.cols[i];
-        const uint8_t* image = L.images + (int64_t)img * L.H * L.Wimg;
+        const bool img_ok = img >= 0 && img < L.n_images;          // (device-pointer entry point: the list is unchecked)
+        const uint8_t* image = L.images + (int64_t)(img_ok ? img : 0) * L.H * L.Wimg;
         for (int e = threadIdx.x; e < per; e += blockDim.x) {
             int r, c;
             bool masked;
@@ -41,7 +42,7 @@ __global__ void gather_image_kernel(GatherLaunch L) {
                 masked = rr >= 2 * W - L.mask_h;
             }
             float v = 0.f;
-            if (!masked && r >= 0 && r < L.H && c >= 0 && c < L.Wimg) v = (float)image[r * L.Wimg + c] - L.mean;
+            if (img_ok && !masked && r >= 0 && r < L.H && c >= 0 && c < L.Wimg) v = (float)image[(int64_t)r * L.Wimg + c] - L.mean;
             if (e < na) act_store<SPLIT>(L.above, i * L.pitch_above + e, v);
             else act_store<SPLIT>(L.left, i * L.pitch_left + (e - na), v);
         }
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(MG5_THREADS, 2) merger_mma_kernel(MergerLaunch
 // In-loop (batch-1) merger: thread = (sample, output o, channel c), c fastest, 80-term fp32 dot product in fixed order.
 // For one sample the tensor-core kernel spends its 21 us preparing 80 KB of weight fragments per CTA; this one reads the
 // 80*16*C weights once, coalesced.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) merger_small_kernel(MergerLaunch L) {
     const int C = L.C;
     const int idx = blockIdx.x * 256 + threadIdx.x;
@@ -581,10 +583,10 @@ __global__ void __launch_bounds__(256) merger_small_kernel(MergerLaunch L) {
     float acc = 0.f;
     const int64_t b0 = (int64_t)s * 48 * C + c, b1 = (int64_t)s * 32 * C + c;
 #pragma unroll 8
-    for (int q = 0; q < 48; ++q) acc = fmaf(act_load<true>(L.in0, b0 + (int64_t)q * C), __ldg(L.w + ((int64_t)q * 16 + o) * C + c), acc);
+    for (int q = 0; q < 48; ++q) acc = fmaf(act_load<SPLIT>(L.in0, b0 + (int64_t)q * C), __ldg(L.w + ((int64_t)q * 16 + o) * C + c), acc);
 #pragma unroll 8
-    for (int q = 0; q < 32; ++q) acc = fmaf(act_load<true>(L.in1, b1 + (int64_t)q * C), __ldg(L.w + ((int64_t)(48 + q) * 16 + o) * C + c), acc);
-    act_store<true>(L.out, ((int64_t)s * 16 + o) * C + c, leaky_relu(acc + __ldg(L.bias + (int64_t)o * C + c)));
+    for (int q = 0; q < 32; ++q) acc = fmaf(act_load<SPLIT>(L.in1, b1 + (int64_t)q * C), __ldg(L.w + ((int64_t)(48 + q) * 16 + o) * C + c), acc);
+    act_store<SPLIT>(L.out, ((int64_t)s * 16 + o) * C + c, leaky_relu(acc + __ldg(L.bias + (int64_t)o * C + c)));
 }
 
 int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
@@ -596,8 +598,9 @@ int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
         cudaFuncSetAttribute(merger_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM);
         g_merger_init = 1;
     }
-    if (L.split && L.in_loop) {
-        merger_small_kernel<<<(L.n * 16 * L.C + 255) / 256, 256, 0, stream>>>(L);
+    if (L.in_loop) {
+        if (L.split) merger_small_kernel<true><<<(L.n * 16 * L.C + 255) / 256, 256, 0, stream>>>(L);
+        else merger_small_kernel<false><<<(L.n * 16 * L.C + 255) / 256, 256, 0, stream>>>(L);
         return 1;
     }
     static const int use_mma = getenv("PNN_MERGER_MMA") ? atoi(getenv("PNN_MERGER_MMA")) != 0 : 1;
@@ -624,12 +627,17 @@ int launch_merger(const MergerLaunch& L, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 __global__ void psnr_kernel(const uint8_t* __restrict__ images, const int32_t* __restrict__ image_index,
                             const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int64_t n,
-                            int H, int Wimg, int W, const uint8_t* __restrict__ pred, double* __restrict__ out) {
+                            int H, int Wimg, int W, const uint8_t* __restrict__ pred, double* __restrict__ out, int n_images) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp0; i < n; i += nwarps) {
         const int img = image_index ? image_index[i] : 0;
+        // a target block that leaves the image (only possible through the unchecked device-pointer entry point): PSNR NaN
+        if (img < 0 || img >= n_images || rows[i] < 0 || cols[i] < 0 || rows[i] + W > H || cols[i] + W > Wimg) {
+            if (lane == 0) out[i] = __longlong_as_double(0x7ff8000000000000LL);
+            continue;
+        }
         const uint8_t* base = images + ((int64_t)img * H + rows[i]) * Wimg + cols[i];
         const uint8_t* p = pred + i * W * W;
         int sse = 0;
@@ -648,9 +656,9 @@ __global__ void psnr_kernel(const uint8_t* __restrict__ images, const int32_t* _
 }
 
 int launch_psnr(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols,
-                int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream) {
+                int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream, int n_images) {
     if (n == 0) return 0;
-    psnr_kernel<<<grid_for(n * 32, 256), 256, 0, stream>>>(images, image_index, rows, cols, n, H, Wimg, W, pred_u8, out);
+    psnr_kernel<<<grid_for(n * 32, 256), 256, 0, stream>>>(images, image_index, rows, cols, n, H, Wimg, W, pred_u8, out, n_images);
     return 1;
 }
 

@@ -797,12 +797,16 @@ void ensure_tiles(pnn_handle* h, Net& net, cudaStream_t stream) {
 }
 
 // Runs every layer of `net` on `n` samples whose contexts are already in the input buffers.
-void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream_t main_stream, bool allow_split_k = false) {
-    const bool split = h->precision == PNN_PRECISION_BF16X3;
+// `in_loop_fp32`: one sample of the codec's in-loop path (convolutional nets).  Every layer runs in fp32 on float buffers
+// whatever the precision of the batched path: the GEMM-shaped layers through launch_gemm_skinny (16 x 16 output tiles over
+// the whole K: no split-K, no reduce launch), the others through the fp32 variants of their kernels.
+void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream_t main_stream, bool allow_split_k = false,
+             bool in_loop_fp32 = false) {
+    const bool split = h->precision == PNN_PRECISION_BF16X3 && !in_loop_fp32;
     // In-loop calls (one sample): the kernels are far too small to fill the GPU, so independent steps run concurrently on
     // lane streams (fork / join with events; inside a stream capture they become parallel branches of the graph).
     static const bool lanes_enabled = !(getenv("PNN_HM_LANES") && atoi(getenv("PNN_HM_LANES")) == 0);
-    const bool lanes = allow_split_k && lanes_enabled && !h->profiling;
+    const bool lanes = (allow_split_k || in_loop_fp32) && lanes_enabled && !h->profiling;
     bool lane_active[4] = {false, false, false, false};
     auto join_lanes = [&]() {
         for (int l = 1; l < 4; ++l) {
@@ -863,7 +867,8 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                     }
                 }
                 ProfScope ps(h, stream, split ? "gemm_tc" : "gemm_fp32", L.M, st.g.N, st.g.K, true);
-                h->launches += split ? launch_gemm_tc(L, stream) : launch_gemm_fp32(L, stream);
+                if (in_loop_fp32) h->launches += launch_gemm_skinny(L, stream);
+                else h->launches += split ? launch_gemm_tc(L, stream) : launch_gemm_fp32(L, stream);
                 if (L.split_k > 1) h->launches += launch_splitk_reduce(L, stream);
                 break;
             }
@@ -875,7 +880,7 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.w = st.d_w32;
                 L.bias = st.d_bias;
                 L.n = (int)n; L.C = st.C; L.split = split;
-                L.in_loop = allow_split_k ? 1 : 0;
+                L.in_loop = (allow_split_k || in_loop_fp32) ? 1 : 0;
                 ProfScope ps(h, stream, "merger", n * st.C, 16, 80, false);
                 h->launches += launch_merger(L, stream);
                 break;
@@ -914,7 +919,7 @@ void check_masks(int W, int mask_w, int mask_h) {
 }
 
 // device-pointer core of the image-block path
-void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int H, int Wimg, const int32_t* d_idx,
+void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int n_images, int H, int Wimg, const int32_t* d_idx,
                          const int32_t* d_rows, const int32_t* d_cols, int64_t n, int mask_w, int mask_h, float* d_f32,
                          uint8_t* d_u8, double* d_psnr, cudaStream_t stream) {
     const int W = net.W;
@@ -930,7 +935,7 @@ void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int H
         G.image_index = d_idx ? d_idx + s0 : nullptr;
         G.rows = d_rows + s0;
         G.cols = d_cols + s0;
-        G.n = m; G.H = H; G.Wimg = Wimg; G.W = W; G.mask_w = mask_w; G.mask_h = mask_h; G.mean = h->mean;
+        G.n = m; G.H = H; G.Wimg = Wimg; G.W = W; G.mask_w = mask_w; G.mask_h = mask_h; G.mean = h->mean; G.n_images = n_images;
         if (net.is_fc) {
             // reference sets/common.py:467-472: flattened above then flattened left in one row
             Act flat = act_of(net, net.in_above);
@@ -965,7 +970,7 @@ void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int H
         run_net(h, net, m, fin, stream);
         if (d_psnr) {
             ProfScope ps(h, stream, "psnr", m * px, 1, 1, false);
-            h->launches += launch_psnr(d_images, G.image_index, G.rows, G.cols, m, H, Wimg, W, u8, d_psnr + s0, stream);
+            h->launches += launch_psnr(d_images, G.image_index, G.rows, G.cols, m, H, Wimg, W, u8, d_psnr + s0, stream, n_images);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -1394,7 +1399,7 @@ int pnn_hevc_best_mode_device(pnn_handle* h, int width, const uint8_t* d_images,
         ensure_device(h);
         ProfScope ps(h, (cudaStream_t)stream, "hevc_best_mode", n, 35, (int64_t)width * width, false);
         h->launches += launch_hevc_best_mode(d_images, d_idx, d_rows, d_cols, n, height, width_image, width, mask_w, mask_h,
-                                             d_best, d_psnr, d_pred, (cudaStream_t)stream);
+                                             d_best, d_psnr, d_pred, (cudaStream_t)stream, n_images);
         CUDA_TRY(cudaGetLastError());
     } catch (const std::exception& e) {
         return fail(h, e);
@@ -1915,7 +1920,12 @@ static void enqueue_hm(pnn_handle* h, Net& net, cudaStream_t s) {
         }
         launches += launch_gather_hm(G, s);
         const int64_t before = h->launches;
-        run_net(h, net, 1, fin, s, /*allow_split_k=*/h->hm_split_k && !net.is_fc);
+        // convolutional nets.  bf16x3 (default): the tensor-core kernels on one sample, their K blocks spread over the SMs
+        // (split-K, fixed slicing) -- measured faster than the fp32 batch-1 layers (CONV-16 / 32 / 64: 104 / 147 / 203 us
+        // against 110 / 203 / 458 us per call); fp32 precision: launch_gemm_skinny, fp32 from end to end.
+        // pnn_set_hm_fused(0): the plain batched kernels.
+        const bool fp32_path = h->precision == PNN_PRECISION_FP32 && h->hm_split_k && !net.is_fc;
+        run_net(h, net, 1, fin, s, /*allow_split_k=*/h->hm_split_k && !net.is_fc && !fp32_path, /*in_loop_fp32=*/fp32_path);
         launches += (int)(h->launches - before);
         h->launches = before;
     }
@@ -2173,7 +2183,8 @@ int pnn_predict_image_blocks_device(pnn_handle* h, int width, int is_fc, const u
         if (n_images > 1 && !d_idx) throw std::runtime_error("`image_index` is NULL while there are several images");
         check_masks(width, mask_w, mask_h);
         ensure_device(h);
-        image_blocks_device(h, *find_net(h, width, is_fc), d_images, height, width_image, d_idx, d_rows, d_cols, n, mask_w,
+        if (n_images <= 0 || height <= 0 || width_image <= 0) throw std::runtime_error("empty image set");
+        image_blocks_device(h, *find_net(h, width, is_fc), d_images, n_images, height, width_image, d_idx, d_rows, d_cols, n, mask_w,
                             mask_h, d_f32, d_u8, d_psnr, (cudaStream_t)stream);
     } catch (const std::exception& e) {
         return fail(h, e);
@@ -2232,7 +2243,7 @@ static int image_blocks_host(pnn_handle* h, int width, int is_fc, const uint8_t*
         for (int64_t s0 = 0; s0 < n; s0 += cap) {
             const int64_t m = std::min(cap, n - s0);
             const bool last = s0 + cap >= n;
-            image_blocks_device(h, net, (const uint8_t*)in.images.p, height, width_image,
+            image_blocks_device(h, net, (const uint8_t*)in.images.p, n_images, height, width_image,
                                 idx ? (const int32_t*)in.idx.p + s0 : nullptr, (const int32_t*)in.rows.p + s0,
                                 (const int32_t*)in.cols.p + s0, m, mask_w, mask_h,
                                 out_f32 ? (float*)net.out_raw.p : nullptr,

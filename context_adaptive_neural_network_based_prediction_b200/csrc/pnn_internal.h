@@ -119,6 +119,7 @@ int launch_make_tc_tiles(const float* w_kn, int K, int N, uint8_t* tiles, cudaSt
 // Each returns the number of kernels it launched.
 // ---------------------------------------------------------------------------------------------
 int launch_gemm_fp32(const GemmLaunch& L, cudaStream_t stream);
+int launch_gemm_skinny(const GemmLaunch& L, cudaStream_t stream);   // batch-1 (in-loop) fp32 layer: 16 x 16 output tiles over the whole K
 int launch_gemm_tc(const GemmLaunch& L, cudaStream_t stream);   // fills the TMA fields itself when the path applies
 void gemm_tc_set_tma(int enabled);
 // one-time opt-in for the tcgen05 kernel's dynamic shared memory
@@ -167,7 +168,7 @@ struct GatherLaunch {
     const int32_t* rows;
     const int32_t* cols;
     int64_t n;
-    int H, Wimg, W, mask_w, mask_h;
+    int H, Wimg, W, mask_w, mask_h, n_images;
     float mean;
     // destination of the above portion [n][W*3W] and of the left portion [n][2W*W]; `pitch_*` in elements
     Act above, left;
@@ -257,7 +258,7 @@ void small_kernels_init();
 // Best HEVC intra mode of every block (35 modes on an unfiltered pattern) -- the baseline of the offline evaluation.
 int launch_hevc_best_mode(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols, int64_t n,
                           int H, int Wimg, int W, int mask_w, int mask_h, uint8_t* best_index, double* psnr, uint8_t* pred,
-                          cudaStream_t stream);
+                          cudaStream_t stream, int n_images);
 
 int launch_win_flags(const double* psnr, const double* baseline, int64_t n, uint8_t* win, cudaStream_t stream);
 
@@ -266,7 +267,7 @@ int launch_convert_input(const float* src, Act dst, int64_t n_elems, int split, 
 
 // PSNR of each block against its target in the image (reference tools/tools.py:364-401).
 int launch_psnr(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols,
-                int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream);
+                int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream, int n_images);
 
 // ---------------------------------------------------------------- weight files (host side)
 // Tensors of one net keyed by the TensorFlow variable names of the reference graph (reference layouts).

@@ -192,6 +192,10 @@ int pnn_synchronize(pnn_handle* h);
 /*
  * Same two calls with DEVICE pointers, asynchronous on `cuda_stream` (a cudaStream_t, may be 0).
  * These are what the throughput numbers with inputs resident in HBM are measured on.
+ * The block list lives on the device, so it cannot be validated here.  Precondition: every block and its context anchor lie
+ * inside its image (what the host-pointer call checks).  A violation is contained, not undefined: context pixels outside the
+ * image (or of an image index outside [0, n_images)) read as masked, and the PSNR of a block that leaves the image is NaN;
+ * pnn_hevc_best_mode_device answers such a block with best_index 255, PSNR NaN and a zero prediction.
  */
 int pnn_predict_batch_device(pnn_handle* h, int width, int is_fully_connected,
                              const float* d_above_or_flat, const float* d_left, int64_t n, float* d_out,

@@ -381,3 +381,31 @@ def test_deferred_creation_and_warm_up(weights_dir, tmp_path):
         plain.close(); lazy.close(); warm.close()
     unused = Engine(paths_file=paths_file, qp_selection=22, deferred=True)
     unused.close()                                            # never touched the device: nothing to tear down
+
+
+@pytest.mark.parametrize('width', [16, 32])
+def test_fp32_in_loop_conv_path(engine, weights_dir, width):
+    """fp32 precision selects the batch-1 fp32 layers for the in-loop convolutional calls (launch_gemm_skinny: 16 x 16 output
+    tiles over the whole K, no split-K): within 1e-3 of the oracle, deterministic."""
+    path, wts = helpers.make_net_file(weights_dir, width, False, seed=270 + width, gain=helpers.GAIN[(width, False)])
+    engine.load_net(path)
+    plane = helpers.synthetic_image(3 * width + 8, 3 * width + 24, 17).astype(numpy.int32)
+    units = 2 * width // 4
+    flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+    flags[units + 1 + units // 2:] = 0
+    n_avail = int(flags.sum())
+    from oracle import context
+    stride = plane.shape[1]
+    _, above, left = context.extract_context_portions_hm(plane.ravel(), stride, (width + 3) * stride + width + 5, flags, n_avail, 4, 4,
+                                                         units, units, width, MEAN)
+    pred, want = _oracle_hm(wts, width, plane, width + 3, width + 5, flags, n_avail)
+    try:
+        engine.set_precision('fp32')
+        raw = engine.predict_hm_context(width, above, left)
+        numpy.testing.assert_array_equal(raw, engine.predict_hm_context(width, above, left))
+        assert numpy.abs(raw - pred).max() <= 1e-3
+        engine.set_context(width, plane, width + 3, width + 5, flags, n_avail)
+        got = engine.predict_hm(width)
+        assert numpy.abs(got - want).max() <= 1 and (got == want).mean() >= 0.999
+    finally:
+        engine.set_precision('bf16x3')

@@ -315,3 +315,36 @@ def test_real_checkpoints_against_float64_loop_goldens(engine, golden_dir, width
             want_u8 = numpy.clip(numpy.round(numpy.clip(gold.astype(numpy.float32) + numpy.float32(MEAN), 0., 255.)), 0, 255).astype(numpy.uint8)
             assert (out['predictions_uint8'] == want_u8).mean() >= 0.999
     engine.set_precision('bf16x3')
+
+
+def test_device_pointer_calls_contain_invalid_blocks(engine, weights_dir):
+    """The device-pointer entry points cannot validate their block lists: a block that leaves the image or names a missing
+    image must not read out of bounds -- its PSNR is NaN (HEVC baseline: index 255), the valid blocks are unaffected."""
+    import torch
+    path, _ = helpers.make_net_file(weights_dir, 8, True, seed=333, gain=1.6)
+    engine.load_net(path)
+    engine.set_precision('bf16x3')
+    images = _image_set(2, 64, 96)
+    dev = torch.device('cuda', 0)
+    rows = numpy.array([8, 16, 60, 8, -5, 24], dtype=numpy.int32)        # 60 + 8 > 64; -5 < 0
+    cols = numpy.array([8, 40, 8, 8, 8, 90], dtype=numpy.int32)          # 90 + 8 > 96
+    idx = numpy.array([0, 1, 0, 7, 1, 1], dtype=numpy.int32)             # image 7 does not exist
+    valid = numpy.array([True, True, False, False, False, False])
+    d_img = torch.from_numpy(images).to(dev)
+    d_r, d_c, d_i = (torch.from_numpy(a).to(dev) for a in (rows, cols, idx))
+    d_u8 = torch.zeros((6, 64), dtype=torch.uint8, device=dev)
+    d_psnr = torch.zeros(6, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    engine.predict_image_blocks_device(8, True, d_img.data_ptr(), 2, 64, 96, d_i.data_ptr(), d_r.data_ptr(), d_c.data_ptr(), 6, (0, 0),
+                                       None, d_u8.data_ptr(), d_psnr.data_ptr(), stream)
+    d_best = torch.zeros(6, dtype=torch.uint8, device=dev)
+    d_hpsnr = torch.zeros(6, dtype=torch.float64, device=dev)
+    engine.hevc_best_mode_device(8, d_img.data_ptr(), 2, 64, 96, d_i.data_ptr(), d_r.data_ptr(), d_c.data_ptr(), 6, (0, 0),
+                                 d_best.data_ptr(), d_hpsnr.data_ptr(), None, stream)
+    torch.cuda.synchronize()
+    psnr, hpsnr, best = d_psnr.cpu().numpy(), d_hpsnr.cpu().numpy(), d_best.cpu().numpy()
+    assert numpy.isnan(psnr[~valid]).all() and numpy.isfinite(psnr[valid]).all()
+    assert numpy.isnan(hpsnr[~valid]).all() and (best[~valid] == 255).all() and (best[valid] < 35).all()
+    ref = engine.predict_image_blocks(8, True, images, rows[valid], cols[valid], idx[valid])
+    numpy.testing.assert_array_equal(d_u8.cpu().numpy()[valid].reshape(-1, 8, 8), ref['predictions_uint8'])
+    numpy.testing.assert_array_equal(psnr[valid], ref['psnrs'])
