@@ -1730,6 +1730,15 @@ static bool persist_start(pnn_handle* h) {
     cudaError_t e;
     {
         std::lock_guard<std::mutex> owner_lock(g_persist_mu);
+        // a process that exits without destroying its handle must not leave a spinning kernel to the driver's teardown
+        static bool at_exit_registered = false;
+        if (!at_exit_registered) {
+            at_exit_registered = true;
+            atexit([] {
+                std::lock_guard<std::mutex> lock(g_persist_mu);
+                if (g_persist_owner) persist_stop_locked(g_persist_owner);
+            });
+        }
         if (g_persist_owner && g_persist_owner != h) persist_stop_locked(g_persist_owner);   // its kernel leaves, ours queues behind
         e = launch_fci_persist(P, h->stream);
         if (e == cudaSuccess) g_persist_owner = h;
