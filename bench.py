@@ -32,7 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WIDTHS = ((4, True), (8, True), (16, False), (32, False))
-N_IMAGES, HEIGHT, WIDTH_IMAGE = 100, 320, 480
+N_IMAGES, HEIGHT, WIDTH_IMAGE = int(os.environ.get('PNN_BENCH_IMAGES', '100')), 320, 480   # (the variable: test aid for ragged shards)
 MEAN = 117.8952234192841
 METRIC = 'PNN predictions/sec (4x4+8x8+16x16+32x32 blocks of 100 BSDS-shaped images)'
 # algorithmic FLOPs per prediction = 2 * MACs (dense count)

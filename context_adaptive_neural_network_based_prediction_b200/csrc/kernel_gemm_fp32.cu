@@ -3,6 +3,8 @@
 // kernel, plain fp32 arithmetic.  Not the throughput path.
 #include "kernels_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace pnn {
 
 namespace {
@@ -105,15 +107,23 @@ __global__ void __launch_bounds__(NT) gemm_fp32_kernel(GemmLaunch L) {
 // a_s[k][16 pixels] (broadcast to the 16 threads of a k) per 16 FMAs.  The 16 k-slices of an output are then added in
 // ascending order.  K is consumed in chunks of SK_CHUNK rows (the implicit-im2col gather of a chunk is staged in shared
 // memory, zero for padding / transposed-convolution borders).  Fixed order, fp32 throughout.
+// A layer is a chain of dependent L2 round trips (one per chunk), so the chunks of a tile are dealt to the CTAs of a
+// THREAD-BLOCK CLUSTER (gridDim.z = cluster size S <= 8, CTA r takes chunks r, r + S, ...): every CTA leaves its 16 x 16
+// partial sums in its own shared memory, and CTA 0 of the cluster adds them in ascending rank through distributed shared
+// memory -- split-K without a partial-sum buffer in global memory, without a second launch and without atomics.
 // ---------------------------------------------------------------------------------------------
 constexpr int SK_CHUNK = 512;
 
 __global__ void __launch_bounds__(256) gemm_skinny_kernel(GemmLaunch L) {
     __shared__ __align__(16) float a_s[SK_CHUNK][16];             // 32 KB
+    __shared__ float part_s[256];                                  // this CTA's partial sums [pixel][channel]
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)blockIdx.z, n_ranks = (int)gridDim.z;
     const GemmGeom& g = L.g;
     const int t = threadIdx.x;
     const int m0 = blockIdx.x * 16, n0 = blockIdx.y * 16;
-    const int ks = t >> 4, n = t & 15;
+    const int ks = t >> 4, n = t & 15;   // (L lives in the constant bank: no copy needed)
     const float* in = (const float*)L.in.p0;
     const float* wcol = L.w_fp32 + n0 + n;
     float acc[16];
@@ -133,13 +143,18 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(GemmLaunch L) {
         g_base = (int64_t)b * g.in_sample_stride;
     }
     const int cin_log2 = 31 - __clz(g.Cin);
-    for (int k0 = 0; k0 < g.K; k0 += SK_CHUNK) {
+    for (int k0 = rank * SK_CHUNK; k0 < g.K; k0 += n_ranks * SK_CHUNK) {
         const int kc = min(SK_CHUNK, g.K - k0);
         // every global load of the chunk is requested up front: the thread's 32 weights (rows ks, ks + 16, ...) and its 8
         // 16-byte pieces of the activation tile; one round trip to L2 per chunk
         float w[SK_CHUNK / 16];
 #pragma unroll
-        for (int u = 0; u < SK_CHUNK / 16; ++u) w[u] = ks + 16 * u < kc ? __ldg(wcol + (int64_t)(k0 + ks + 16 * u) * g.N) : 0.f;
+        for (int u = 0; u < SK_CHUNK / 16; ++u) {
+            // volatile asm, row index clamped: unconditional loads that keep their place before the barrier (left alone, ptxas
+            // sinks every load next to its FMAs: 32 dependent L2 round trips per chunk)
+            const int kk = min(ks + 16 * u, kc - 1);
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(w[u]) : "l"(wcol + (int64_t)(k0 + kk) * g.N));
+        }
         float4 v[SK_CHUNK / 64];
 #pragma unroll
         for (int j = 0; j < SK_CHUNK / 64; ++j) {
@@ -152,7 +167,8 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(GemmLaunch L) {
                 const int iy = g_oy * g.sy_o + tyy * g.sy_t + g.cy;
                 const int ix = g_ox * g.sx_o + txx * g.sx_t + g.cx;
                 if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) {
-                    v[j] = __ldg(reinterpret_cast<const float4*>(in + g_base + (((int64_t)iy * g.IW + ix) << cin_log2) + ci));
+                    const float* src = in + g_base + (((int64_t)iy * g.IW + ix) << cin_log2) + ci;
+                    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w) : "l"(src));
                 }
             }
         }
@@ -192,6 +208,17 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(GemmLaunch L) {
     float sum = 0.f;
 #pragma unroll
     for (int s = 0; s < 16; ++s) sum += red[(s * 16 + p) * 16 + n];
+    if (n_ranks > 1) {
+        // partial sums of the cluster's CTAs, added by CTA 0 in ascending rank (distributed shared memory)
+        part_s[t] = sum;
+        cluster.sync();
+        if (rank == 0) {
+            sum = 0.f;
+            for (int r = 0; r < n_ranks; ++r) sum += cluster.map_shared_rank(part_s, r)[t];
+        }
+        cluster.sync();                                           // nobody leaves while its shared memory may still be read
+        if (rank != 0) return;
+    }
     const int m = m0 + p, nn = n0 + n;
     if (m >= L.M || nn >= g.N) return;
     float v = sum + L.bias[nn];
@@ -207,8 +234,21 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(GemmLaunch L) {
 
 int launch_gemm_skinny(const GemmLaunch& L, cudaStream_t stream) {
     if (L.M == 0) return 0;
-    dim3 grid((L.M + 15) / 16, (L.g.N + 15) / 16);
-    gemm_skinny_kernel<<<grid, 256, 0, stream>>>(L);
+    const int chunks = (L.g.K + SK_CHUNK - 1) / SK_CHUNK;
+    const int ranks = chunks < 8 ? chunks : 8;                    // portable cluster size
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((L.M + 15) / 16, (L.g.N + 15) / 16, ranks);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = ranks;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, gemm_skinny_kernel, L);
     return 1;
 }
 
