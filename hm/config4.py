@@ -43,6 +43,8 @@ def main():
     args = ap.parse_args()
     out = {'config': 'configs[3]: HM-16.15 substitution encoder + decoder, first-frame intra, synthetic 1920x1080 4:0:0, QP ' + args.qps,
            'host_cores': os.cpu_count()}
+    # a small encode first: the first CUDA process on a fresh box pays the driver's cold start (seconds), which belongs to no arm
+    run('direct', '32', ['--width', '416', '--height', '240'])
     runs = {}
     for name, backend, extra in (('regular', 'regular', ()), ('gpu_direct', 'direct', ()), ('gpu_seam', 'cuda', ()),
                                  ('cpu_all_threads', 'cpu', ()), ('cpu_best_threads', 'cpu', ('--ref-threads', args.best_threads))):
