@@ -17,44 +17,65 @@ static inline int grid_for(int64_t n, int block) {
 // :467-472 FC flattening = above row-major then left row-major).
 // ---------------------------------------------------------------------------------------------
 template <bool SPLIT>
-__global__ void gather_image_kernel(GatherLaunch L) {
-    // blockDim = (64, 4): threadIdx.y picks the block (target patch), threadIdx.x strides over its 5*W*W pixels
+__global__ void __launch_bounds__(256) gather_image_kernel(GatherLaunch L) {
+    // thread = four consecutive pixels of one context row of one block: rows are 3W (above) or W (left) pixels long, both
+    // multiples of four, and so are the masks, so a chunk is masked as a whole; one 8-byte store per bf16 plane (or one
+    // 16-byte fp32 store) per thread instead of four 2-byte ones
     const int W = L.W;
-    const int na = 3 * W * W, per = 5 * W * W, w3 = 3 * W;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y; i < L.n; i += (int64_t)gridDim.x * blockDim.y) {
+    const int ca = 3 * W / 4, cl = W / 4;                    // chunks per row
+    const int na4 = W * ca, per4 = na4 + 2 * W * cl;         // chunks per block: above, total
+    const int64_t total = L.n * per4;
+    for (int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x; gid < total; gid += (int64_t)gridDim.x * 256) {
+        const int64_t i = gid / per4;
+        const int q = (int)(gid - i * per4);
         const int img = L.image_index ? L.image_index[i] : 0;
         const int r0 = L.rows[i], c0 = L.cols[i];
-        const bool img_ok = img >= 0 && img < L.n_images;          // (device-pointer entry point: the list is unchecked)
+        const bool img_ok = img >= 0 && img < L.n_images;      // (device-pointer entry point: the list is unchecked)
         const uint8_t* image = L.images + (int64_t)(img_ok ? img : 0) * L.H * L.Wimg;
-        for (int e = threadIdx.x; e < per; e += blockDim.x) {
-            int r, c;
-            bool masked;
-            if (e < na) {
-                const int rr = e / w3, cc = e - rr * w3;
-                r = r0 - W + rr;
-                c = c0 - W + cc;
-                masked = cc >= w3 - L.mask_w;
-            } else {
-                const int e2 = e - na;
-                const int rr = e2 / W, cc = e2 - rr * W;
-                r = r0 + rr;
-                c = c0 - W + cc;
-                masked = rr >= 2 * W - L.mask_h;
+        int r, c, e;
+        bool masked;
+        const bool is_above = q < na4;
+        if (is_above) {
+            const int rr = q / ca, cc = (q - rr * ca) * 4;
+            r = r0 - W + rr;
+            c = c0 - W + cc;
+            masked = cc >= 3 * W - L.mask_w;
+            e = rr * 3 * W + cc;
+        } else {
+            const int q2 = q - na4;
+            const int rr = q2 / cl, cc = (q2 - rr * cl) * 4;
+            r = r0 + rr;
+            c = c0 - W + cc;
+            masked = rr >= 2 * W - L.mask_h;
+            e = rr * W + cc;
+        }
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (img_ok && !masked && r >= 0 && r < L.H) {
+            const uint8_t* src = image + (int64_t)r * L.Wimg;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c + j >= 0 && c + j < L.Wimg) v[j] = (float)src[c + j] - L.mean;
             }
-            float v = 0.f;
-            if (img_ok && !masked && r >= 0 && r < L.H && c >= 0 && c < L.Wimg) v = (float)image[(int64_t)r * L.Wimg + c] - L.mean;
-            if (e < na) act_store<SPLIT>(L.above, i * L.pitch_above + e, v);
-            else act_store<SPLIT>(L.left, i * L.pitch_left + (e - na), v);
+        }
+        const Act& dst = is_above ? L.above : L.left;
+        const int64_t o = i * (is_above ? L.pitch_above : L.pitch_left) + e;
+        if (SPLIT) {
+            uint32_t hi[2], lo[2];
+            split_bf16x2(v[0], v[1], hi[0], lo[0]);
+            split_bf16x2(v[2], v[3], hi[1], lo[1]);
+            *reinterpret_cast<uint2*>((__nv_bfloat16*)dst.p0 + o) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>((__nv_bfloat16*)dst.p1 + o) = make_uint2(lo[0], lo[1]);
+        } else {
+            *reinterpret_cast<float4*>((float*)dst.p0 + o) = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
 
 int launch_gather_image(const GatherLaunch& L, cudaStream_t stream) {
     if (L.n == 0) return 0;
-    const dim3 block(64, 4);
-    const int grid = grid_for(L.n * 64, 64);   // one (64-thread) row per target patch
-    if (L.split) gather_image_kernel<true><<<grid, block, 0, stream>>>(L);
-    else gather_image_kernel<false><<<grid, block, 0, stream>>>(L);
+    const int grid = grid_for(L.n * (5 * L.W * L.W / 4), 256);
+    if (L.split) gather_image_kernel<true><<<grid, 256, 0, stream>>>(L);
+    else gather_image_kernel<false><<<grid, 256, 0, stream>>>(L);
     return 1;
 }
 
@@ -298,8 +319,59 @@ __global__ void __launch_bounds__(128) col2im_kernel(Col2imLaunch L) {
     final_store(L.fin, (int64_t)b * P + pix, acc + L.bias);
 }
 
+// The same with the sample's per-tap products staged in shared memory first (maps up to 16 x 16 input pixels, i.e. every net
+// but CONV-64): the global reads become contiguous 8- / 16-byte loads instead of one scattered 2-byte load per tap and plane
+// (1.0 -> ms per bench step).  Same tap order, same arithmetic.
+constexpr int C2I_MAX = 8192;
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) col2im_smem_kernel(Col2imLaunch L) {
+    __shared__ __align__(16) float d_s[C2I_MAX];
+    const int n_in = L.IH * L.IW * L.NP;                      // a multiple of 16
+    const int64_t base = (int64_t)blockIdx.x * n_in;
+    for (int idx = threadIdx.x * 4; idx < n_in; idx += 256 * 4) {
+        float4 v;
+        if (SPLIT) {
+            const uint2 h = __ldg(reinterpret_cast<const uint2*>((const __nv_bfloat16*)L.d.p0 + base + idx));
+            const uint2 l = __ldg(reinterpret_cast<const uint2*>((const __nv_bfloat16*)L.d.p1 + base + idx));
+            v.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+            v.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+            v.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+            v.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+        } else {
+            v = __ldg(reinterpret_cast<const float4*>((const float*)L.d.p0 + base + idx));
+        }
+        *reinterpret_cast<float4*>(d_s + idx) = v;
+    }
+    __syncthreads();
+    const int OH = L.IH * L.stride, OW = L.IW * L.stride, P = OH * OW;
+    for (int pix = threadIdx.x; pix < P; pix += 256) {
+        const int y = pix / OW, x = pix - y * OW;
+        float acc = 0.f;
+        for (int ky = 0; ky < L.k; ++ky) {
+            const int ty = y + L.pad - ky;
+            if (ty < 0 || (L.stride == 2 && (ty & 1))) continue;
+            const int iy = L.stride == 2 ? ty >> 1 : ty;
+            if (iy >= L.IH) continue;
+            for (int kx = 0; kx < L.k; ++kx) {
+                const int tx = x + L.pad - kx;
+                if (tx < 0 || (L.stride == 2 && (tx & 1))) continue;
+                const int ix = L.stride == 2 ? tx >> 1 : tx;
+                if (ix >= L.IW) continue;
+                acc += d_s[(iy * L.IW + ix) * L.NP + ky * L.k + kx];
+            }
+        }
+        final_store(L.fin, (int64_t)blockIdx.x * P + pix, acc + L.bias);
+    }
+}
+
 int launch_col2im(const Col2imLaunch& L, cudaStream_t stream) {
     if (L.n == 0) return 0;
+    if (L.IH * L.IW * L.NP <= C2I_MAX) {
+        if (L.split) col2im_smem_kernel<true><<<(unsigned)L.n, 256, 0, stream>>>(L);
+        else col2im_smem_kernel<false><<<(unsigned)L.n, 256, 0, stream>>>(L);
+        return 1;
+    }
     const int P = L.IH * L.stride * L.IW * L.stride;
     const int64_t grid = (int64_t)L.n * ((P + 127) / 128);
     if (L.split) col2im_kernel<true><<<(unsigned)grid, 128, 0, stream>>>(L);
@@ -655,9 +727,44 @@ __global__ void psnr_kernel(const uint8_t* __restrict__ images, const int32_t* _
     }
 }
 
+// Blocks of 4 x 4 and 8 x 8 pixels: one THREAD per block (a warp per block leaves half / none of its lanes busy and the
+// bench has 1.2 M such blocks).  Same integer sum, same formula.
+__global__ void __launch_bounds__(256) psnr_small_kernel(const uint8_t* __restrict__ images, const int32_t* __restrict__ image_index,
+                                                         const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int64_t n,
+                                                         int H, int Wimg, int W, const uint8_t* __restrict__ pred, double* __restrict__ out,
+                                                         int n_images) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int img = image_index ? image_index[i] : 0;
+        if (img < 0 || img >= n_images || rows[i] < 0 || cols[i] < 0 || rows[i] + W > H || cols[i] + W > Wimg) {
+            out[i] = __longlong_as_double(0x7ff8000000000000LL);
+            continue;
+        }
+        const uint8_t* base = images + ((int64_t)img * H + rows[i]) * Wimg + cols[i];
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(pred + i * W * W);     // W*W is a multiple of 16 bytes
+        int sse = 0;
+        for (int r = 0; r < W; ++r) {
+            const uint8_t* row = base + (int64_t)r * Wimg;
+            for (int c4 = 0; c4 < W; c4 += 4) {
+                const uint32_t q = __ldg(p + (r * W + c4) / 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int d = (int)row[c4 + j] - (int)((q >> (8 * j)) & 0xffu);
+                    sse += d * d;
+                }
+            }
+        }
+        const double mse = (double)sse / (double)(W * W);
+        out[i] = 10. * log10(255. * 255. / (mse + 1.e-6));
+    }
+}
+
 int launch_psnr(const uint8_t* images, const int32_t* image_index, const int32_t* rows, const int32_t* cols,
                 int64_t n, int H, int Wimg, int W, const uint8_t* pred_u8, double* out, cudaStream_t stream, int n_images) {
     if (n == 0) return 0;
+    if (W <= 8) {
+        psnr_small_kernel<<<grid_for(n, 256), 256, 0, stream>>>(images, image_index, rows, cols, n, H, Wimg, W, pred_u8, out, n_images);
+        return 1;
+    }
     psnr_kernel<<<grid_for(n * 32, 256), 256, 0, stream>>>(images, image_index, rows, cols, n, H, Wimg, W, pred_u8, out, n_images);
     return 1;
 }
