@@ -346,3 +346,42 @@ def test_torch_oracle_against_float64_loop_goldens(golden_dir, width):
         gold = g['pred_%d_m%d%d' % (width, masks[0], masks[1])]
         assert numpy.abs(gold).max() > 50.
         assert numpy.abs(pred - gold).max() <= 5e-4
+
+
+def test_cpu_baseline_backend_matches_the_oracle(tmp_path):
+    """oracle/_ref/libpnn_ref.so -- the libtorch-CPU backend behind the C ABI that stands in for the reference's TensorFlow-CPU HM
+    build (baseline leg of configs[3]) -- computes the oracle's predictions: same layers, in process, batch of one."""
+    import os
+    import helpers
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path_lib = os.path.join(root, 'oracle', '_ref', 'libpnn_ref.so')
+    if not os.path.exists(path_lib):
+        pytest.skip('oracle/_ref/libpnn_ref.so has not been built (needs the libtorch headers)')
+    lib = ctypes.CDLL(path_lib)
+    lib.pnn_create.argtypes = [ctypes.c_char_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    lib.pnn_load_net.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.pnn_predict_hm_context.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.pnn_destroy.argtypes = [ctypes.c_void_p]
+    h = ctypes.c_void_p()
+    assert lib.pnn_create(None, ctypes.c_float(MEAN), 22, 0, ctypes.byref(h)) == 0
+    assert lib.pnn_create(None, ctypes.c_float(MEAN), 0, 0, ctypes.byref(ctypes.c_void_p())) == -1     # QP must be positive
+    try:
+        for width, is_fc in ((4, True), (8, True), (16, False)):
+            path, wts = helpers.make_net_file(str(tmp_path), width, is_fc, seed=width, gain=helpers.GAIN[(width, is_fc)])
+            assert lib.pnn_load_net(h, path.encode()) == 0
+            rng = numpy.random.default_rng(width)
+            above = rng.normal(0., 40., (width, 3 * width)).astype(numpy.float32)
+            left = rng.normal(0., 40., (2 * width, width)).astype(numpy.float32)
+            out = numpy.zeros((width, width), dtype=numpy.float32)
+            if is_fc:
+                flat = numpy.concatenate([above.ravel(), left.ravel()])
+                assert lib.pnn_predict_hm_context(h, width, flat.ctypes.data, None, out.ctypes.data) == 0
+                ref = nets.forward_fc(wts, flat[None])[0, :, :, 0]
+            else:
+                assert lib.pnn_predict_hm_context(h, width, above.ctypes.data, left.ctypes.data, out.ctypes.data) == 0
+                ref = nets.forward_conv(wts, above[None, :, :, None], left[None, :, :, None])[0, :, :, 0]
+            assert numpy.abs(ref).max() > 1.
+            assert numpy.abs(out - ref).max() <= 1e-4
+        assert lib.pnn_predict_hm_context(h, 32, above.ctypes.data, left.ctypes.data, out.ctypes.data) == -1   # no such net
+    finally:
+        lib.pnn_destroy(h)
