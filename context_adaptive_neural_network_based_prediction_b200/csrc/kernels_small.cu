@@ -259,6 +259,159 @@ __global__ void __launch_bounds__(CF_THREADS, PR == 4 ? 3 : 5) conv_first_all_gr
     }
 }
 
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    // not volatile: the accumulator dependency alone fixes the summation order, independent chains may interleave
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// bf16x3 precision, batched calls: the same convolution as an im2col product [16 pixels x K*K] x [K*K x C] per warp on
+// the tensor cores (mma.sync, register fragments: a tcgen05 operand would need the im2col rows written to shared memory
+// in the K-major UMMA layout first, and with one input channel there is no 16-byte inner box for TMA).  ONE launch
+// writes all C channels, so the input is read once instead of once per 16-channel group.  Per warp and tile of 16
+// pixels: 8 (K = 3: 4) predicated LDG per lane and pixel row -- issued one tile AHEAD, so their latency hides behind
+// the current tile --, hi/lo split of the taps, (C / 8) x ceil(K*K / 16) x 3 mma (hi*hi, hi*lo, lo*hi, k ascending:
+// fixed order) on accumulators that start at the bias, LeakyReLU + split, a swizzled shared-memory transpose and
+// 16-byte stores (a tile's 16 pixels are 2 KB contiguous in each plane).  The weight fragments are split once per CTA
+// into shared memory in per-lane order (one conflict-free LDS.128 per (k step, channel octet)): in registers they cost
+// 64 of them and a fourth of the resident warps.  Fragment layout: see merger_mma_kernel below.
+struct FastDiv {                                   // n / d for n < 2^31 (host: fast_div_make)
+    uint32_t mul, shift, d;
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : __umulhi(n, f.mul) >> f.shift; }
+static FastDiv fast_div_make(uint32_t d) {
+    FastDiv f{0, 0, d};
+    if (d <= 1) return f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                   // ceil(log2 d) >= 1
+    f.mul = (uint32_t)(((1ull << (31 + l)) / d) + 1);
+    f.shift = l - 1;
+    return f;
+}
+
+template <int K, int S, int NT>
+__global__ void __launch_bounds__(CF_THREADS, 4) conv_first_mma_kernel(const __grid_constant__ ConvFirstLaunch L,
+                                                                       const __grid_constant__ ConvFirstWeights Wt,
+                                                                       const __grid_constant__ FastDiv divP,
+                                                                       const __grid_constant__ FastDiv divOW) {
+    constexpr int KK = K * K, KS = (KK + 15) / 16, NSLOT = KS * 4, WARPS = CF_THREADS / 32;
+    __shared__ __align__(16) uint32_t stage[WARPS][2][16 * NT * 4];
+    __shared__ __align__(16) uint4 wfrag[KS * NT * 32];            // {b0_hi, b1_hi, b0_lo, b1_lo} per (k step, octet, lane)
+    __shared__ float2 sbias[NT * 4];                               // the accumulators start at the bias
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int idx = threadIdx.x; idx < KS * NT * 32; idx += CF_THREADS) {
+        const int ln = idx & 31, j = (idx >> 5) % NT, ks = idx / (32 * NT);
+        const int n = j * 8 + (ln >> 2), k0 = ks * 16 + 2 * (ln & 3);
+        float w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = k0 + (i & 1) + (i >> 1) * 8;
+            w[i] = k < KK ? Wt.w[k * 64 + n] : 0.f;
+        }
+        uint4 f;
+        split_bf16x2(w[0], w[1], f.x, f.z);
+        split_bf16x2(w[2], w[3], f.y, f.w);
+        wfrag[idx] = f;
+    }
+    // the K*K taps this lane feeds: slot 4*ks + {0, 1, 2, 3} = k 16*ks + 2t + {0, 1, 8, 9}
+    int tap_off[NSLOT], tap_yx[NSLOT];
+#pragma unroll
+    for (int sl = 0; sl < NSLOT; ++sl) {
+        const int k = (sl >> 2) * 16 + 2 * t + (sl & 1) + ((sl & 2) ? 8 : 0);
+        const int ky = k / K, kx = k - ky * K;
+        tap_yx[sl] = k < KK ? (ky << 16 | kx) : (0x4000 << 16);    // a tap beyond K*K is never in range: value 0
+        tap_off[sl] = ky * L.IW + kx;
+    }
+    if (threadIdx.x < NT * 4) sbias[threadIdx.x] = make_float2(Wt.b[2 * threadIdx.x], Wt.b[2 * threadIdx.x + 1]);
+    __syncthreads();
+    const uint32_t P = (uint32_t)(L.OH * L.OW), M = (uint32_t)L.n * P, tiles = (M + 15) >> 4;
+    const uint32_t step = gridDim.x * WARPS;
+    uint32_t* st_hi = stage[warp][0];
+    uint32_t* st_lo = stage[warp][1];
+    const uint4* wf = wfrag + lane;
+
+    // the 2 x NSLOT taps of (tile, lane): rows g and g + 8
+    auto load_taps = [&](uint32_t tile, float (&v)[2][NSLOT]) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t pix = (tile << 4) + g + 8 * r;
+            const bool pix_ok = pix < M;
+            const uint32_t b = fast_div(pix, divP), rem = pix - b * P;
+            const uint32_t oy = fast_div(rem, divOW), ox = rem - oy * (uint32_t)L.OW;
+            const int iy0 = (int)oy * S - L.pad, ix0 = (int)ox * S - L.pad;
+            const float* base = L.in + (int64_t)b * (L.IH * L.IW) + iy0 * L.IW + ix0;
+#pragma unroll
+            for (int sl = 0; sl < NSLOT; ++sl) {
+                const bool ok = pix_ok && (unsigned)(iy0 + (tap_yx[sl] >> 16)) < (unsigned)L.IH &&
+                                (unsigned)(ix0 + (tap_yx[sl] & 0xffff)) < (unsigned)L.IW;
+                v[r][sl] = ok ? __ldg(base + tap_off[sl]) : 0.f;
+            }
+        }
+    };
+
+    uint32_t tile = blockIdx.x * WARPS + warp;
+    float v[2][NSLOT];
+    if (tile < tiles) load_taps(tile, v);
+    for (; tile < tiles; tile += step) {
+        uint32_t ah[KS][4], al[KS][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                split_bf16x2(v[r][4 * ks], v[r][4 * ks + 1], ah[ks][r], al[ks][r]);
+                split_bf16x2(v[r][4 * ks + 2], v[r][4 * ks + 3], ah[ks][2 + r], al[ks][2 + r]);
+            }
+        if (tile + step < tiles) load_taps(tile + step, v);        // in flight during this tile's products and stores
+        __syncwarp();                                              // the previous tile's staged rows have been read
+#pragma unroll
+        for (int j0 = 0; j0 < NT; j0 += 4) {                       // 4 independent accumulator chains in flight
+            float acc[4][4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const float2 bj = sbias[(j0 + jj) * 4 + t];
+                acc[jj][0] = bj.x; acc[jj][1] = bj.y; acc[jj][2] = bj.x; acc[jj][3] = bj.y;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint4 b[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) b[jj] = wf[(ks * NT + j0 + jj) * 32];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_bf16_16816(acc[jj], ah[ks], b[jj].x, b[jj].y);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_bf16_16816(acc[jj], ah[ks], b[jj].z, b[jj].w);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) mma_bf16_16816(acc[jj], al[ks], b[jj].x, b[jj].y);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    uint32_t hi, lo;
+                    split_bf16x2(fmaxf(acc[jj][2 * r], 0.1f * acc[jj][2 * r]), fmaxf(acc[jj][2 * r + 1], 0.1f * acc[jj][2 * r + 1]), hi, lo);
+                    const int row = g + 8 * r, word = ((j0 + jj) * 4 + t) ^ ((g & (NT - 1)) << 2);   // 16-byte chunk index XOR row: no bank conflicts at C = 64
+                    st_hi[row * (NT * 4) + word] = hi;
+                    st_lo[row * (NT * 4) + word] = lo;
+                }
+        }
+        __syncwarp();
+        constexpr int CHUNKS = NT;                                 // 16-byte chunks per row and plane
+#pragma unroll
+        for (int it = 0; it < 16 * CHUNKS / 32; ++it) {
+            const int idx = it * 32 + lane, row = idx / CHUNKS, chunk = idx - row * CHUNKS;
+            const uint32_t pix = (tile << 4) + row;
+            if (pix < M) {
+                const int phys = chunk ^ (row & (NT - 1));
+                const uint4 vh = *reinterpret_cast<const uint4*>(st_hi + row * (NT * 4) + phys * 4);
+                const uint4 vl = *reinterpret_cast<const uint4*>(st_lo + row * (NT * 4) + phys * 4);
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)L.out.p0 + (int64_t)pix * (NT * 8) + chunk * 8) = vh;
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)L.out.p1 + (int64_t)pix * (NT * 8) + chunk * 8) = vl;
+            }
+        }
+    }
+}
+
 template <int K, int S, bool SPLIT, int PR>
 void conv_first_launch_groups(const ConvFirstLaunch& L, const ConvFirstWeights& W, unsigned grid, cudaStream_t stream) {
     if (grid <= 148) {
@@ -273,8 +426,22 @@ void conv_first_launch_groups(const ConvFirstLaunch& L, const ConvFirstWeights& 
     }
 }
 
+template <int K, int S>
+static void conv_first_launch_mma(const ConvFirstLaunch& L, const ConvFirstWeights& W, cudaStream_t stream) {
+    const int64_t tiles = ((int64_t)L.n * L.OH * L.OW + 15) >> 4;
+    const unsigned grid = (unsigned)std::min<int64_t>((tiles + CF_THREADS / 32 - 1) / (CF_THREADS / 32), 148 * 4);   // persistent: 4 CTAs / SM
+    const FastDiv dp = fast_div_make((uint32_t)(L.OH * L.OW)), dw = fast_div_make((uint32_t)L.OW);
+    if (L.C == 64) conv_first_mma_kernel<K, S, 8><<<grid, CF_THREADS, 0, stream>>>(L, W, dp, dw);
+    else conv_first_mma_kernel<K, S, 4><<<grid, CF_THREADS, 0, stream>>>(L, W, dp, dw);
+}
+
 int launch_conv_first(const ConvFirstLaunch& L, const ConvFirstWeights& W, cudaStream_t stream) {
     if (L.n == 0) return 0;
+    if (L.split && !L.in_loop && (int64_t)L.n * L.OH * L.OW < (1ll << 31) - 16) {   // every batched bf16x3 call, whatever its size: one arithmetic per block
+        if (L.k == 5 && L.stride == 2) conv_first_launch_mma<5, 2>(L, W, stream);
+        else conv_first_launch_mma<3, 1>(L, W, stream);
+        return 1;
+    }
     constexpr int PR = 2;
     const int64_t total = (int64_t)L.n * (L.OH / PR) * L.OW;
     const unsigned grid = (unsigned)std::min<int64_t>((total + CF_THREADS - 1) / CF_THREADS, 148 * 20);
@@ -526,11 +693,6 @@ void small_kernels_init() {
 // same SM; persistent over sample tiles.  Fragment layout (PTX ISA, m16n8k16 .bf16): g = lane >> 2, t = lane & 3;
 // A: a0 (row g, k 2t..2t+1), a1 (row g+8, same k), a2 (row g, k 2t+8..2t+9), a3 (row g+8, k 2t+8..); B: b0 (k 2t..2t+1,
 // n g), b1 (k 2t+8.., n g); C: c0, c1 (row g, n 2t, 2t+1), c2, c3 (row g+8, same n).
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ uint32_t u4_word(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
 __global__ void __launch_bounds__(MG5_THREADS, 2) merger_mma_kernel(MergerLaunch L, int groups) {

@@ -891,6 +891,7 @@ void run_net(pnn_handle* h, Net& net, int64_t n, const FinalOut& fin, cudaStream
                 L.out = act_of(net, st.out);
                 L.n = (int)n; L.IH = st.IH; L.IW = st.IW; L.OH = st.OH; L.OW = st.OW; L.C = st.C; L.k = st.k;
                 L.stride = st.stride; L.pad = st.pad; L.split = split;
+                L.in_loop = (allow_split_k || in_loop_fp32) ? 1 : 0;
                 ProfScope ps(h, stream, "conv_first", n * st.OH * st.OW, st.C, st.k * st.k, false);
                 h->launches += launch_conv_first(L, *st.conv_first, stream);
                 break;

@@ -136,8 +136,10 @@ struct ConvFirstLaunch {
     const float* in;     // [n, IH, IW] fp32
     Act out;             // [n*OH*OW, C]
     int n, IH, IW, OH, OW, C, k, stride, pad, split;
+    int in_loop;         // 1: batch-1 call of the codec (keeps the direct fp32 FFMA kernel, like PNN_PRECISION_FP32)
 };
-// One launch per group of 16 output channels (C / 16 launches); returns the number of launches.
+// Batched bf16x3 calls: one tensor-core launch for all channels.  fp32 precision and in-loop calls: direct FFMA kernels,
+// one launch per group of 16 output channels (or one in all for small grids).  Returns the number of launches.
 int launch_conv_first(const ConvFirstLaunch& L, const ConvFirstWeights& W, cudaStream_t stream);
 
 // col2im of the last transposed convolution + the output epilogue: D[(b, iy, ix), ky*k+kx] holds the
