@@ -314,13 +314,15 @@ __global__ void __launch_bounds__(CF_THREADS, 4) conv_first_mma_kernel(const __g
         split_bf16x2(w[2], w[3], f.y, f.w);
         wfrag[idx] = f;
     }
-    // the K*K taps this lane feeds: slot 4*ks + {0, 1, 2, 3} = k 16*ks + 2t + {0, 1, 8, 9}
-    int tap_off[NSLOT], tap_yx[NSLOT];
+    // the K*K taps this lane feeds: slot 4*ks + {0, 1, 2, 3} = k 16*ks + 2t + {0, 1, 8, 9}; a tap is read when its row bit
+    // (ky) and its column bit (8 + kx) are both set in the pixel's mask of in-range rows and columns
+    int tap_off[NSLOT];
+    uint32_t tap_need[NSLOT];
 #pragma unroll
     for (int sl = 0; sl < NSLOT; ++sl) {
         const int k = (sl >> 2) * 16 + 2 * t + (sl & 1) + ((sl & 2) ? 8 : 0);
         const int ky = k / K, kx = k - ky * K;
-        tap_yx[sl] = k < KK ? (ky << 16 | kx) : (0x4000 << 16);    // a tap beyond K*K is never in range: value 0
+        tap_need[sl] = k < KK ? (1u << ky | 1u << (8 + kx)) : 0x80000000u;    // a tap beyond K*K is never in range: value 0
         tap_off[sl] = ky * L.IW + kx;
     }
     if (threadIdx.x < NT * 4) sbias[threadIdx.x] = make_float2(Wt.b[2 * threadIdx.x], Wt.b[2 * threadIdx.x + 1]);
@@ -336,17 +338,16 @@ __global__ void __launch_bounds__(CF_THREADS, 4) conv_first_mma_kernel(const __g
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const uint32_t pix = (tile << 4) + g + 8 * r;
-            const bool pix_ok = pix < M;
             const uint32_t b = fast_div(pix, divP), rem = pix - b * P;
             const uint32_t oy = fast_div(rem, divOW), ox = rem - oy * (uint32_t)L.OW;
             const int iy0 = (int)oy * S - L.pad, ix0 = (int)ox * S - L.pad;
-            const float* base = L.in + (int64_t)b * (L.IH * L.IW) + iy0 * L.IW + ix0;
+            // rows max(0, -iy0) .. min(K, IH - iy0) - 1 and the same for the columns are inside the input
+            const uint32_t rows = (0xffffffffu << max(0, -iy0)) & ~(0xffffffffu << min(K, L.IH - iy0));
+            const uint32_t cols = (0xffffffffu << max(0, -ix0)) & ~(0xffffffffu << min(K, L.IW - ix0));
+            const uint32_t have = pix < M ? (rows | cols << 8) : 0u;
+            const int off = (int)b * (L.IH * L.IW) + iy0 * L.IW + ix0;     // launcher: n * IH * IW < 2^31
 #pragma unroll
-            for (int sl = 0; sl < NSLOT; ++sl) {
-                const bool ok = pix_ok && (unsigned)(iy0 + (tap_yx[sl] >> 16)) < (unsigned)L.IH &&
-                                (unsigned)(ix0 + (tap_yx[sl] & 0xffff)) < (unsigned)L.IW;
-                v[r][sl] = ok ? __ldg(base + tap_off[sl]) : 0.f;
-            }
+            for (int sl = 0; sl < NSLOT; ++sl) v[r][sl] = (~have & tap_need[sl]) == 0u ? __ldg(L.in + (off + tap_off[sl])) : 0.f;
         }
     };
 
@@ -437,7 +438,7 @@ static void conv_first_launch_mma(const ConvFirstLaunch& L, const ConvFirstWeigh
 
 int launch_conv_first(const ConvFirstLaunch& L, const ConvFirstWeights& W, cudaStream_t stream) {
     if (L.n == 0) return 0;
-    if (L.split && !L.in_loop && (int64_t)L.n * L.OH * L.OW < (1ll << 31) - 16) {   // every batched bf16x3 call, whatever its size: one arithmetic per block
+    if (L.split && !L.in_loop && (int64_t)L.n * L.OH * L.OW < (1ll << 31) - 16 && (int64_t)L.n * L.IH * L.IW < (1ll << 31)) {   // every batched bf16x3 call, whatever its size: one arithmetic per block
         if (L.k == 5 && L.stride == 2) conv_first_launch_mma<5, 2>(L, W, stream);
         else conv_first_launch_mma<3, 1>(L, W, stream);
         return 1;
