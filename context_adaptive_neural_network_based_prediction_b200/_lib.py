@@ -18,6 +18,7 @@ EXPORTS = (
     'pnn_profile_report', 'pnn_debug_time_gemm', 'pnn_predict_hm_context', 'pnn_set_hm_fused', 'pnn_hevc_best_mode', 'pnn_hevc_best_mode_device',
     'pnn_inspect_net_file', 'pnn_predict_image_blocks_async', 'pnn_synchronize',
     'pnn_set_hm_cache', 'pnn_hm_cache_stats', 'pnn_set_workspace_budget', 'pnn_register_net', 'pnn_set_context_lazy', 'pnn_create_deferred', 'pnn_release_at_exit', 'pnn_warm_up',
+    'pnn_predict_hm_begin',
 )
 
 PRECISION_FP32 = 0
@@ -62,6 +63,8 @@ def load():
     lib.pnn_set_context.restype = i32
     lib.pnn_predict_hm.argtypes = [vp, i32, vp, i32]
     lib.pnn_predict_hm.restype = i32
+    lib.pnn_predict_hm_begin.argtypes = [vp, i32]
+    lib.pnn_predict_hm_begin.restype = i32
     lib.pnn_predict_batch.argtypes = [vp, i32, i32, vp, vp, i64, vp]
     lib.pnn_predict_batch.restype = i32
     lib.pnn_predict_image_blocks.argtypes = [vp, i32, i32, vp, i32, i32, i32, vp, vp, vp, i64, i32, i32, vp, vp, vp]

@@ -617,6 +617,14 @@ struct pnn_handle {
         uint8_t flags[2 * 64 + 1];
     } hm_desc;
     bool hm_desc_pending = false;            // the pixels of hm_desc are not staged yet (pnn_set_context_lazy)
+    struct HmInflight {                      // pnn_predict_hm_begin: ONE in-loop request posted to the GPU, not collected yet
+        bool active = false;
+        bool answered = false;               // the memo held the result at posting time: nothing is running
+        bool persistent = false;             // posted to the persistent FC kernel (else: the net's graph was launched)
+        Net* net = nullptr;
+        uint64_t tag = 0;                    // memo slot of the staged context (hm_staged stays untouched until the collect)
+        size_t slot = 0;
+    } hm_inflight;
     bool hm_lazy_context = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float hm_ms = 0.f;
@@ -671,8 +679,15 @@ static void drop_hm_caches(pnn_handle* h) {
     for (auto& kv : h->nets) kv.second->cache = Net::HmCache();
 }
 
+extern "C" {
+static void hm_drain(pnn_handle* h);   // defined with the in-loop path below
+}
 struct Quiesce {   // entry points that use the GPU for anything but an in-loop FC call
-    explicit Quiesce(pnn_handle* h) { if (h) persist_stop(h); }
+    explicit Quiesce(pnn_handle* h) {
+        if (!h) return;
+        hm_drain(h);            // a request posted by pnn_predict_hm_begin is answered (and remembered) first
+        persist_stop(h);
+    }
 };
 
 namespace {
@@ -1250,6 +1265,7 @@ int pnn_release_at_exit(pnn_handle* h) {
     if (!h->device_ready) return 0;
     Trace trace("pnn_release_at_exit");
     cudaSetDevice(h->device);
+    hm_drain(h);
     persist_stop(h);
     cudaDeviceSynchronize();
     return 0;
@@ -1290,6 +1306,7 @@ void pnn_destroy(pnn_handle* h) {
     }
     Trace trace("pnn_destroy");
     cudaSetDevice(h->device);
+    hm_drain(h);
     persist_stop(h);
     cudaDeviceSynchronize();
     h->nets.clear();
@@ -1662,7 +1679,10 @@ int pnn_set_context(pnn_handle* h, int width, const int32_t* roi_origin, int pic
         memcpy(d.flags, flags, (size_t)(above_units + left_units + 1));
         h->hm_desc_pending = true;
         h->hm_width = width;
-        if (!h->hm_lazy_context) stage_context(h);   // lazy: pnn_predict_hm copies the pixels, if it is ever called
+        if (!h->hm_lazy_context) {   // lazy: pnn_predict_hm copies the pixels, if it is ever called
+            hm_drain(h);             // the staged context is the memo key of a request in flight
+            stage_context(h);
+        }
     } catch (const std::exception& e) {
         h->hm_width = 0;
         return fail(h, e);
@@ -1758,8 +1778,9 @@ static bool persist_start(pnn_handle* h) {
 
 // One in-loop FC prediction through the persistent kernel: the staged context goes out as {payload, seq} pairs, the
 // outputs come back the same way (8-byte accesses are single-copy atomic on both sides).
-static void run_hm_fc_persist(pnn_handle* h, Net& net) {
-    const int W = net.W, K0 = 5 * W * W, n_out = W * W;
+// Posts the staged context to the persistent FC kernel; fc_collect polls the answer.
+static void fc_post(pnn_handle* h, Net& net) {
+    const int W = net.W, K0 = 5 * W * W;
     const int32_t* staged = h->hm_staged;
     const unsigned seq = h->fc_seq = next_seq(h->fc_seq);
     volatile uint64_t* req = h->fci_req;
@@ -1835,6 +1856,11 @@ static void run_hm_fc_persist(pnn_handle* h, Net& net) {
     }
     req_store(req + 0, cmd, seq);
     h->fc_calls_since_stop += 1;
+}
+
+static void fc_collect(pnn_handle* h, Net& net) {
+    const int W = net.W, n_out = W * W;
+    const unsigned seq = h->fc_seq;
     long long spins = 0;
     bool warned = false;
     const std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
@@ -1942,8 +1968,9 @@ static void enqueue_hm(pnn_handle* h, Net& net, cudaStream_t s) {
     net.hm_launches = launches;
 }
 
-// Replays the captured launch sequence of `net` on the staged context (captures it on first use).
-static void run_hm_graph(pnn_handle* h, Net& net) {
+// Replays the captured launch sequence of `net` on the staged context (captures it on first use); graph_collect waits
+// for it.
+static void graph_post(pnn_handle* h, Net& net) {
     const bool restart = h->persist_running && h->fc_calls_since_stop > 0;   // FC calls are interleaved with this net's
     persist_stop(h);
     ensure_workspace(net, 1);
@@ -1984,6 +2011,9 @@ static void run_hm_graph(pnn_handle* h, Net& net) {
     // the codec alternates this net with hundreds of FC calls: bring the persistent kernel back behind the graph, while
     // the host goes on with the result
     if (restart) persist_start(h);
+}
+
+static void graph_collect(pnn_handle* h, Net& net) {
     CUDA_TRY(cudaEventSynchronize(h->ev1));
     h->launches += net.hm_launches;
     CUDA_TRY(cudaEventElapsedTime(&h->hm_ms, h->ev0, h->ev1));
@@ -2008,13 +2038,18 @@ static uint64_t hash_words(const int32_t* p, size_t n) {
     return hsh ? hsh : 1ull;
 }
 
-static void run_hm(pnn_handle* h, Net& net) {
+// Posts the staged context: looks it up in the memo, else hands it to the persistent FC kernel / launches the net's graph.
+// Does not wait: hm_collect does, and remembers the answer.  hm_staged must stay untouched in between.
+static void hm_post(pnn_handle* h, Net& net) {
     if (h->persist_stale.exchange(false)) persist_stop(h);    // the warm-up thread added an FC net: relaunch with it
     const int W = net.W;
     const size_t key_words = (size_t)HM_HEADER_INTS + 5 * W * W, out_words = (size_t)2 * W * W;
     Net::HmCache& c = net.cache;
-    uint64_t tag = 0;
-    size_t slot = 0;
+    pnn_handle::HmInflight& f = h->hm_inflight;
+    f.net = &net;
+    f.answered = false;
+    f.tag = 0;
+    f.slot = 0;
     if (h->hm_cache) {
         if (c.entries == 0) {
             // about 16 MB per net
@@ -2025,25 +2060,57 @@ static void run_hm(pnn_handle* h, Net& net) {
             c.keys.resize(c.entries * key_words);
             c.outs.resize(c.entries * out_words);
         }
-        tag = hash_words(h->hm_staged, key_words);
-        slot = (size_t)(tag % c.entries);
-        if (c.tags[slot] == tag && memcmp(c.keys.data() + slot * key_words, h->hm_staged, key_words * 4) == 0) {
-            memcpy(h->hm_out_raw, c.outs.data() + slot * out_words, (size_t)W * W * 4);
-            memcpy(h->hm_out, c.outs.data() + slot * out_words + W * W, (size_t)W * W * 4);
+        f.tag = hash_words(h->hm_staged, key_words);
+        f.slot = (size_t)(f.tag % c.entries);
+        if (c.tags[f.slot] == f.tag && memcmp(c.keys.data() + f.slot * key_words, h->hm_staged, key_words * 4) == 0) {
+            memcpy(h->hm_out_raw, c.outs.data() + f.slot * out_words, (size_t)W * W * 4);
+            memcpy(h->hm_out, c.outs.data() + f.slot * out_words + W * W, (size_t)W * W * 4);
             h->hm_cache_hits += 1;
             h->hm_ms = 0.f;
+            f.answered = true;
+            f.active = true;
             return;
         }
         h->hm_cache_misses += 1;
     }
-    if (net.is_fc && net.fci_images && persist_wanted(h) && persist_start(h)) run_hm_fc_persist(h, net);
-    else run_hm_graph(h, net);
-    if (h->hm_cache) {
-        c.tags[slot] = tag;
-        memcpy(c.keys.data() + slot * key_words, h->hm_staged, key_words * 4);
-        memcpy(c.outs.data() + slot * out_words, h->hm_out_raw, (size_t)W * W * 4);
-        memcpy(c.outs.data() + slot * out_words + W * W, h->hm_out, (size_t)W * W * 4);
+    f.persistent = net.is_fc && net.fci_images && persist_wanted(h) && persist_start(h);
+    if (f.persistent) fc_post(h, net);
+    else graph_post(h, net);
+    f.active = true;
+}
+
+static void hm_collect(pnn_handle* h) {
+    pnn_handle::HmInflight& f = h->hm_inflight;
+    if (!f.active) return;
+    f.active = false;                       // (also when the wait below throws: the request is given up)
+    if (f.answered) return;
+    Net& net = *f.net;
+    if (f.persistent) fc_collect(h, net);
+    else graph_collect(h, net);
+    if (h->hm_cache && net.cache.entries) {
+        Net::HmCache& c = net.cache;
+        const int W = net.W;
+        c.tags[f.slot] = f.tag;
+        memcpy(c.keys.data() + f.slot * c.key_words, h->hm_staged, c.key_words * 4);
+        memcpy(c.outs.data() + f.slot * c.out_words, h->hm_out_raw, (size_t)W * W * 4);
+        memcpy(c.outs.data() + f.slot * c.out_words + W * W, h->hm_out, (size_t)W * W * 4);
     }
+}
+
+// A request in flight whose answer nobody is waiting for yet: finish it so that the GPU, the doorbell and hm_staged are
+// free again; the answer stays in the memo (the codec usually asks for it later: the RD pass repeats the fast pass's TU).
+static void hm_drain(pnn_handle* h) {
+    if (!h->hm_inflight.active) return;
+    try {
+        hm_collect(h);
+    } catch (const std::exception& e) {
+        h->error = e.what();
+    }
+}
+
+static void run_hm(pnn_handle* h, Net& net) {
+    hm_post(h, net);
+    hm_collect(h);
 }
 
 // the net that serves in-loop calls of this width: fully-connected if one is loaded (the reference's choice for widths 4
@@ -2063,13 +2130,33 @@ int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
     try {
         if (!dst) throw std::runtime_error("`piPred` is NULL.");
         if (h->hm_width != width) throw std::runtime_error("pnn_predict_hm called without a matching pnn_set_context");
-        ensure_device(h);
-        Net& net = hm_net(h, width);
         const int W = width;
-        if (h->hm_desc_pending) stage_context(h);
-        run_hm(h, net);
+        if (h->hm_inflight.active && h->hm_inflight.net->W == width && !h->hm_desc_pending) {
+            hm_collect(h);                 // pnn_predict_hm_begin posted exactly this context
+        } else {
+            hm_drain(h);
+            ensure_device(h);
+            Net& net = hm_net(h, width);
+            if (h->hm_desc_pending) stage_context(h);
+            run_hm(h, net);
+        }
         // reference TComPrediction.cpp(substitution):626-635: row-major copy with HM's stride
         for (int i = 0; i < W; ++i) memcpy(dst + (int64_t)i * dst_stride, h->hm_out + i * W, W * sizeof(int32_t));
+    } catch (const std::exception& e) {
+        return fail(h, e);
+    }
+    return 0;
+}
+
+int pnn_predict_hm_begin(pnn_handle* h, int width) {
+    if (!h) return -1;
+    try {
+        if (h->hm_width != width) throw std::runtime_error("pnn_predict_hm_begin called without a matching pnn_set_context");
+        hm_drain(h);
+        ensure_device(h);
+        Net& net = hm_net(h, width);
+        if (h->hm_desc_pending) stage_context(h);
+        hm_post(h, net);
     } catch (const std::exception& e) {
         return fail(h, e);
     }
@@ -2079,6 +2166,7 @@ int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride) {
 int pnn_predict_hm_context(pnn_handle* h, int width, const float* above_or_flat, const float* left, float* out) {
     if (!h) return -1;
     try {
+        hm_drain(h);
         if (!above_or_flat || !out) throw std::runtime_error("NULL buffer");
         if (width != 4 && width != 8 && width != 16 && width != 32 && width != 64) {
             throw std::runtime_error("the width of the TB does not belong to {4, 8, 16, 32, 64}");
@@ -2120,6 +2208,7 @@ int pnn_set_workspace_budget(pnn_handle* h, int64_t bytes_per_net) {
 
 int pnn_set_hm_cache(pnn_handle* h, int enabled) {
     if (!h) return -1;
+    hm_drain(h);
     h->hm_cache = enabled != 0;
     if (!h->hm_cache) drop_hm_caches(h);
     return 0;

@@ -275,6 +275,10 @@ class Engine(object):
         self._check(self._lib.pnn_predict_hm_context(self._h, width, _ptr(a), _ptr(l), _ptr(out)))
         return out
 
+    def predict_hm_begin(self, width):
+        """Posts the context of the last `set_context` to the GPU and returns at once; `predict_hm` collects the answer."""
+        self._check(self._lib.pnn_predict_hm_begin(self._h, width))
+
     def predict_hm(self, width, dst_stride=None):
         """NN branch of predIntraAng: returns the int32 [W, W] prediction (HM rounding)."""
         stride = width if dst_stride is None else dst_stride

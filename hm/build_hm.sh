@@ -68,7 +68,8 @@ for V in $VARIANTS; do
   mkdir -p "$OBJ"
   cp -rs "$SRC" "$MIRROR"
   rm -f "$MIRROR/Lib/TLibCommon/TComPrediction.h" "$MIRROR/Lib/TLibCommon/TComPrediction.cpp" "$MIRROR/Lib/TLibCommon/TComPattern.cpp"
-  python "$ROOT/hm/direct/patch_hm.py" "$SRC/Lib/TLibCommon" "$MIRROR/Lib/TLibCommon" || exit 1
+  rm -f "$MIRROR/Lib/TLibEncoder/TEncSearch.cpp"
+  python "$ROOT/hm/direct/patch_hm.py" "$SRC/Lib/TLibCommon" "$MIRROR/Lib/TLibCommon" "$SRC/Lib/TLibEncoder" "$MIRROR/Lib/TLibEncoder" || exit 1
   SRC="$MIRROR"
   FLAGS="-O3 -std=c++11 -DMSYS_LINUX -w -include cmath -I$ROOT/hm/direct -I$ROOT/include -I$SRC/Lib -I$SRC/Lib/TLibCommon -I$COMMON"
   LIBSRCS=$(ls $SRC/Lib/TLibCommon/*.cpp $SRC/Lib/TLibVideoIO/*.cpp $SRC/Lib/TLibEncoder/*.cpp $SRC/Lib/TLibDecoder/*.cpp $SRC/Lib/TAppCommon/*.cpp)

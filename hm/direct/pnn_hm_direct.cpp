@@ -17,6 +17,20 @@ pnn_handle* g_handle = NULL;
 long long g_calls[5] = {0, 0, 0, 0, 0};
 double g_seconds[5] = {0., 0., 0., 0., 0.};
 double g_first_seconds[5] = {0., 0., 0., 0., 0.};   // the first call of a width: device initialisation (first width) and the upload of the net
+long long g_posts[5] = {0, 0, 0, 0, 0};             // requests posted ahead of their use (prefetch)
+bool g_first_done[5] = {false, false, false, false, false};
+
+int width_index(int width) { return width == 4 ? 0 : width == 8 ? 1 : width == 16 ? 2 : width == 32 ? 3 : 4; }
+
+// host time spent inside the library for one width: posting and collecting both count
+void account(int index, double dt) {
+    if (!g_first_done[index]) {
+        g_first_done[index] = true;
+        g_first_seconds[index] = dt;
+    } else {
+        g_seconds[index] += dt;
+    }
+}
 
 void print_stats() {
     const char* path = getenv("PNN_HM_STATS");
@@ -28,8 +42,8 @@ void print_stats() {
         // the first call of a width waits for the device initialisation / the upload of its net: counted in the total, kept out
         // of the per-call figure
         const long long later(g_calls[i] > 1 ? g_calls[i] - 1 : 0);
-        fprintf(f, "pnn_calls width %d: %lld calls, %.6f s, %.2f us/call (first call %.1f ms, not in the per-call figure)\n", 4 << i,
-                g_calls[i], g_seconds[i] + g_first_seconds[i], later ? 1.e6 * g_seconds[i] / later : 0., 1.e3 * g_first_seconds[i]);
+        fprintf(f, "pnn_calls width %d: %lld calls, %.6f s, %.2f us/call (first call %.1f ms, not in the per-call figure; %lld posted ahead)\n", 4 << i,
+                g_calls[i], g_seconds[i] + g_first_seconds[i], later ? 1.e6 * g_seconds[i] / later : 0., 1.e3 * g_first_seconds[i], g_posts[i]);
         total += g_calls[i];
         seconds += g_seconds[i] + g_first_seconds[i];
     }
@@ -112,6 +126,22 @@ int set_context(pnn_handle* handle, int width, const int* piRoiOrigin, int iPicS
     return code;
 }
 
+int prefetch(pnn_handle* handle, int width) {
+    static const bool enabled(getenv("PNN_HM_PREFETCH") ? atoi(getenv("PNN_HM_PREFETCH")) != 0 : true);
+    if (!enabled) return 0;
+    const std::chrono::steady_clock::time_point t0(std::chrono::steady_clock::now());
+    const int code(pnn_predict_hm_begin(handle, width));
+    const double dt(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    if (code != 0) {
+        fprintf(stderr, "%s\n", pnn_last_error(handle));
+        return code;
+    }
+    const int index(width_index(width));
+    account(index, dt);
+    g_posts[index] += 1;
+    return 0;
+}
+
 int predict(pnn_handle* handle, int width, int* piPred, int stride) {
     const std::chrono::steady_clock::time_point t0(std::chrono::steady_clock::now());
     const int code(pnn_predict_hm(handle, width, piPred, stride));
@@ -120,9 +150,8 @@ int predict(pnn_handle* handle, int width, int* piPred, int stride) {
         fprintf(stderr, "%s\n", pnn_last_error(handle));
         return code;
     }
-    const int index(static_cast<int>(std::log2(static_cast<double>(width))) - 2);
-    if (g_calls[index] == 0) g_first_seconds[index] = dt;
-    else g_seconds[index] += dt;
+    const int index(width_index(width));
+    account(index, dt);
     g_calls[index] += 1;
     return 0;
 }

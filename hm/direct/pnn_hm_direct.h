@@ -6,6 +6,7 @@
 //   TComPrediction::initTempBuff   (TComPrediction.cpp(substitution):108-236)  -> read_mean_file + create
 //   initIntraPatternChType         (TComPattern.cpp:342-380)                   -> set_context   (pnn_set_context)
 //   predIntraAng, NN branch        (TComPrediction.cpp:556-635)                -> predict       (pnn_predict_hm)
+//   estIntraPredLumaQT, fast pass  (TEncSearch.cpp:2332-2342), one inserted call  -> prefetch      (pnn_predict_hm_begin)
 // Unlike the link seam of hm/shim/ (which only replaces Session::Run), the context gather / masking / mean subtraction
 // and the add-mean / clip / round epilogue run inside the library here.
 #ifndef PNN_HM_DIRECT_H
@@ -28,6 +29,12 @@ pnn_handle* create(const std::string& path_to_file_paths_to_graphs_output, float
 // extract_context_portions' arguments (extraction_context.h:36-48) without the destination buffers
 int set_context(pnn_handle* handle, int width, const int* piRoiOrigin, int iPicStride, const bool* bNeighborFlags,
                 int iNumIntraNeighbor, int iUnitWidth, int iUnitHeight, int iAboveUnits, int iLeftUnits);
+
+// Fast pass of the intra search (TEncSearch.cpp(substitution):2332-2393), right after initIntraPatternChType: the context
+// of the PU is final, the neural-network mode is evaluated further down (substitution: mode 18 of the loop; switch: mode 35
+// of the RD list) -> the request is posted now (pnn_predict_hm_begin) and computes while the host predicts and costs the
+// other modes.  PNN_HM_PREFETCH=0 turns it off (A/B measurements with one executable).
+int prefetch(pnn_handle* handle, int width);
 
 // NN branch of predIntraAng: prediction of the staged context into HM's Pel buffer
 int predict(pnn_handle* handle, int width, int* piPred, int stride);

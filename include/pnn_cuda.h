@@ -139,6 +139,18 @@ int pnn_set_context_lazy(pnn_handle* h, int enabled);
 int pnn_predict_hm(pnn_handle* h, int width, int32_t* dst, int dst_stride);
 
 /*
+ * Optional step 1b: posts the context of the last pnn_set_context to the GPU and returns at once, so that the codec's own
+ * work hides the latency of the call.  In the fast pass of the intra search (TEncSearch.cpp(substitution):2332-2393) the
+ * context is final once initIntraPatternChType has run, the neural-network mode is number 18 of the 35 the loop
+ * evaluates: the request travels and computes while the host predicts and costs modes 0..17.  A pnn_predict_hm of the
+ * same width that follows without another pnn_set_context collects the answer; any other call first finishes the request
+ * and keeps its answer in the memo of in-loop results (pnn_set_hm_cache), where the RD pass of the switch codec -- which
+ * evaluates mode 35 for the very transform block the fast pass just looked at (TEncSearch.cpp(switch):2476-2491) -- finds
+ * it.  Nothing is speculative: the context is the final one, the bits are those of pnn_predict_hm.  One request in flight.
+ */
+int pnn_predict_hm_begin(pnn_handle* h, int width);
+
+/*
  * In-loop call with an already extracted context: what Session::Run does in the reference's HM
  * (TComPrediction.cpp(substitution):572-579 / 601-608) after extract_context_portions filled the
  * batch-1 input tensors (TComPattern.cpp:366-380).  FC nets: `above_or_flat` is [5*W*W], `left` NULL;

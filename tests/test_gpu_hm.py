@@ -409,3 +409,59 @@ def test_fp32_in_loop_conv_path(engine, weights_dir, width):
         assert numpy.abs(got - want).max() <= 1 and (got == want).mean() >= 0.999
     finally:
         engine.set_precision('bf16x3')
+
+
+@pytest.mark.parametrize('width', [4, 8, 16, 64])
+def test_posted_request_is_collected_or_remembered(engine, weights_dir, width):
+    """pnn_predict_hm_begin posts the context and returns; a pnn_predict_hm that follows collects the answer (same bits as the
+    synchronous call); any other call first finishes the request and leaves its answer in the memo, where the same context is
+    found again (the switch codec's RD pass after the fast pass)."""
+    is_fc = width <= 8
+    path, _ = helpers.make_net_file(weights_dir, width, is_fc, seed=400 + width, gain=helpers.GAIN[(width, is_fc)])
+    engine.load_net(path)
+    units = 2 * width // 4
+    flags = numpy.ones(2 * units + 1, dtype=numpy.uint8)
+    n_avail = int(flags.sum())
+    planes = [helpers.synthetic_image(3 * width + 8, 3 * width + 24, 50 + i).astype(numpy.int32) for i in range(3)]
+    sync = []
+    for plane in planes:
+        engine.set_context(width, plane, width + 2, width + 4, flags, n_avail)
+        sync.append(engine.predict_hm(width).copy())
+    assert not numpy.array_equal(sync[0], sync[1])
+    try:
+        engine.set_context_lazy(True)
+        engine.set_hm_cache(True)
+        hits0, misses0 = engine.hm_cache_stats
+        # 1. begin ... predict: collected
+        engine.set_context(width, planes[0], width + 2, width + 4, flags, n_avail)
+        engine.predict_hm_begin(width)
+        numpy.testing.assert_array_equal(engine.predict_hm(width), sync[0])
+        # 2. begin, then ANOTHER context: the posted request is finished and remembered, the new one is computed
+        engine.set_context(width, planes[1], width + 2, width + 4, flags, n_avail)
+        engine.predict_hm_begin(width)
+        engine.set_context(width, planes[2], width + 2, width + 4, flags, n_avail)
+        numpy.testing.assert_array_equal(engine.predict_hm(width), sync[2])
+        hits1, misses1 = engine.hm_cache_stats
+        assert (hits1 - hits0, misses1 - misses0) == (0, 3)
+        # ... and the remembered one is answered from the memo, whether asked for directly or through another begin
+        engine.set_context(width, planes[1], width + 2, width + 4, flags, n_avail)
+        numpy.testing.assert_array_equal(engine.predict_hm(width), sync[1])
+        engine.set_context(width, planes[1], width + 2, width + 4, flags, n_avail)
+        engine.predict_hm_begin(width)
+        numpy.testing.assert_array_equal(engine.predict_hm(width), sync[1])
+        hits2, misses2 = engine.hm_cache_stats
+        assert (hits2 - hits1, misses2 - misses1) == (2, 0)
+        # 3. begin, then a batched call on the same handle: no dead-lock, both right
+        engine.set_hm_cache(False)
+        engine.set_context(width, planes[0], width + 2, width + 4, flags, n_avail)
+        engine.predict_hm_begin(width)
+        engine.synchronize()
+        engine.set_context(width, planes[0], width + 2, width + 4, flags, n_avail)
+        numpy.testing.assert_array_equal(engine.predict_hm(width), sync[0])
+        # 4. begin needs a context
+        from context_adaptive_neural_network_based_prediction_b200 import PnnError
+        with pytest.raises(PnnError):
+            engine.predict_hm_begin(width * 2 if width < 64 else 4)
+    finally:
+        engine.set_hm_cache(False)
+        engine.set_context_lazy(False)
