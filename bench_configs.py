@@ -117,8 +117,10 @@ def run_hm(args, emit):
                    'pnn_encoder': gpu['pnn_encoder']},
         'roofline': {'bound': 'hbm', 'kernel': 'fci_persist_kernel (FC-4 in-loop call)', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s',
                      'frac': gbs / peak, 'traffic': None,
-                     'note': 'parameter bytes (12.0 MB) / wall time of one call through the codec; the weights stay in shared memory, so '
-                             'this is an equivalent bandwidth, bounded by the PCIe doorbell round trips and three all-to-all exchanges'},
+                     'note': 'parameter bytes (12.0 MB) / host time of one call inside the library (posting + collecting: the direct binding '
+                             'posts the request at the start of the fast pass, so part of the ~9 us latency hides behind the codec); the '
+                             'weights stay in shared memory, so this is an equivalent bandwidth, bounded by the PCIe doorbell round trips and '
+                             'three all-to-all exchanges'},
         'cpu_baseline': {'value': cpu['encoder_wall_s'], 'unit': 's/frame', 'cores': cpu['host_cores'], 'kind': 'port',
                          'sample': 'the same codec objects linked against oracle/_ref/libpnn_ref.so (libtorch-CPU, FC nets 8 threads, '
                                    'convolutional nets 16 threads: the fastest setting of tools/ref_backend_latency.py), same frame, same QP',

@@ -17,10 +17,10 @@ sys.path.insert(0, ROOT)
 from context_adaptive_neural_network_based_prediction_b200 import rd
 
 
-def run(backend, qps, extra=(), timeout=1500):
+def run(backend, qps, extra=(), timeout=1500, env=None):
     cmd = [sys.executable, os.path.join(ROOT, 'hm', 'run_hm.py'), '--qps', qps] + list(extra)
     cmd += ['--variant', 'regular'] if backend == 'regular' else ['--backend', backend]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
     rows = [json.loads(l) for l in p.stdout.splitlines() if l.startswith('{')]
     for r in rows:
         if 'error' in r:
@@ -29,7 +29,7 @@ def run(backend, qps, extra=(), timeout=1500):
 
 
 def brief(rows):
-    keys = ('qp', 'encoder_wall_s', 'encoder_total_time_s', 'decoder_wall_s', 'decoder_total_time_s', 'bytes', 'y_psnr_kbps',
+    keys = ('qp', 'encoder_wall_s', 'encoder_total_time_s', 'decoder_wall_s', 'decoder_total_time_s', 'bytes', 'bitstream_md5', 'y_psnr_kbps',
             'decoder_hash_ok', 'recon_enc_equals_dec', 'pnn_encoder', 'pnn_decoder')
     return [{k: r.get(k) for k in keys} for r in rows]
 
@@ -46,19 +46,24 @@ def main():
     # a small encode first: the first CUDA process on a fresh box pays the driver's cold start (seconds), which belongs to no arm
     run('direct', '32', ['--width', '416', '--height', '240'])
     runs = {}
-    for name, backend, extra in (('regular', 'regular', ()), ('gpu_direct', 'direct', ()), ('gpu_seam', 'cuda', ()),
+    # gpu_direct: the direct binding, neural-network requests posted at the start of the fast pass (pnn_predict_hm_begin);
+    # gpu_direct_no_prefetch: the same executable with PNN_HM_PREFETCH=0; gpu_seam: unmodified codec sources (link seam)
+    for name, backend, extra in (('regular', 'regular', ()), ('gpu_direct', 'direct', ()), ('gpu_direct_no_prefetch', 'direct', ()),
+                                 ('gpu_seam', 'cuda', ()),
                                  ('cpu_all_threads', 'cpu', ()), ('cpu_best_threads', 'cpu', ('--ref-threads', args.best_threads))):
-        runs[name] = run(backend, args.qps, extra)
+        runs[name] = run(backend, args.qps, extra, env={'PNN_HM_PREFETCH': '0'} if name == 'gpu_direct_no_prefetch' else None)
         out[name] = brief(runs[name])
         print(name, [(r['qp'], round(r['encoder_wall_s'], 2)) for r in runs[name]], file=sys.stderr, flush=True)
     summary = {}
-    for gpu in ('gpu_direct', 'gpu_seam'):
+    for gpu in ('gpu_direct', 'gpu_direct_no_prefetch', 'gpu_seam'):
         for cpu in ('cpu_all_threads', 'cpu_best_threads'):
             summary['encoder_wall_ratio_%s_over_%s' % (cpu, gpu)] = {
                 str(a['qp']): b['encoder_wall_s'] / a['encoder_wall_s'] for a, b in zip(runs[gpu], runs[cpu])}
         summary['bjontegaard_percent_%s_vs_cpu' % gpu] = rd.compare_runs(runs[gpu], runs['cpu_best_threads'], 1080, 1920) \
             if len(runs[gpu]) >= 4 else None
         summary['identical_bitstream_sizes_%s_vs_cpu' % gpu] = all(a['bytes'] == b['bytes'] for a, b in zip(runs[gpu], runs['cpu_best_threads']))
+        summary['identical_bitstreams_md5_%s_vs_gpu_seam' % gpu] = all(a['bitstream_md5'] == b['bitstream_md5'] for a, b in zip(runs[gpu], runs['gpu_seam']))
+        summary['identical_bitstreams_md5_%s_vs_cpu' % gpu] = all(a['bitstream_md5'] == b['bitstream_md5'] for a, b in zip(runs[gpu], runs['cpu_best_threads']))
     summary['all_hash_ok'] = all(r['decoder_hash_ok'] and r['recon_enc_equals_dec'] for k in runs if k != 'regular' for r in runs[k])
     out['summary'] = summary
     if not args.skip_real:

@@ -5,7 +5,7 @@ hm/shim/), with seeded random-init PNN weights (the pretrained HM weights are no
 and prints one JSON object per QP: wall times, HM's own "Total Time", PNN call statistics per block width,
 decoder picture-hash status and whether encoder and decoder reconstructions are byte-identical.
 """
-import argparse, json, os, pickle, re, subprocess, sys, tempfile, time
+import argparse, hashlib, json, os, pickle, re, subprocess, sys, tempfile, time
 import numpy
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -101,7 +101,7 @@ for qp in [int(q) for q in args.qps.split(',')]:
         'backend': args.backend, 'host_cores': os.cpu_count(), 'ref_threads': args.ref_threads,
         'trained_small_nets': args.trained_small_nets, 'qp': qp, 'encoder_wall_s': t_enc, 'encoder_total_time_s': float(enc_total[0]) if enc_total else None,
         'decoder_wall_s': t_dec, 'decoder_total_time_s': float(dec_total[0]) if dec_total else None,
-        'bytes': int(bits[0]) if bits else None, 'y_psnr_kbps': psnr[0] if psnr else None,
+        'bytes': int(bits[0]) if bits else None, 'bitstream_md5': hashlib.md5(open(bit, 'rb').read()).hexdigest() if os.path.exists(bit) else None, 'y_psnr_kbps': psnr[0] if psnr else None,
         'decoder_rc': d.returncode, 'decoder_hash_ok': '(OK)' in d.stdout and 'ERROR' not in d.stdout,
         'recon_enc_equals_dec': same, 'pnn_encoder': enc_stats,
         'pnn_decoder': open(stats_d).read().strip().split('\n') if os.path.exists(stats_d) else [],
