@@ -88,7 +88,8 @@ def patch_search_cpp(text):
     """TEncSearch::estIntraPredLumaQT, fast pass.
 
     1. One inserted call after initIntraPatternChType: the request of the neural-network mode is posted.
-    2. Substitution codec (the neural-network mode is number 18 of the loop): the loop visits the modes in the order
+    2. After the mode loop: the request of the PU's top-left quadrant (the next PU the codec evaluates at this position) is posted.
+    3. Substitution codec (the neural-network mode is number 18 of the loop): the loop visits the modes in the order
        0..17, 19..34, 18 and only stores their costs; the candidate list is then updated in the ORIGINAL order 0..34.  The
        iterations are independent (the prediction buffer is scratch, xModeBitsIntra reloads the entropy-coder state, the
        list update is the only carried state), so the list -- ties included -- and the bitstream are those of the
@@ -128,6 +129,35 @@ def patch_search_cpp(text):
     return text, (j, len(loop_head), k, len(update))
 
 
+POST_LOOP = '''      // libpnn_cuda: the top-left quadrant of this PU is the first PU the codec looks at next at this position (first CU of the
+      // next depth, or the first NxN PU); all of its context lies outside this PU, so it is final already: post its request
+      // now, it computes during the RD pass of this PU and waits in the memo of in-loop results.  The memo is keyed by the
+      // whole context, availability included: a context that turns out different later is simply computed again.
+      if (contextFlag && puRect.width >= 8)
+      {
+        TComTURecurse tuFirstQuadrant(tuRecurseWithPU, false, TComTU::QUAD_SPLIT);
+        bool contextFlagFirstQuadrant(false);
+        initIntraPatternChType(tuFirstQuadrant,
+                               contextFlagFirstQuadrant,
+                               COMPONENT_Y,
+                               true DEBUG_STRING_PASS_INTO(sTemp2));
+        if (contextFlagFirstQuadrant)
+        {
+          const int error_code_prefetch(pnn_hm_direct::prefetch_first_quadrant(m_pnn, static_cast<int>(puRect.width / 2)));
+          if (error_code_prefetch < 0)
+          {
+            assert(false);
+          }
+        }
+      }
+'''
+
+
+def add_post_loop(text, where):
+    j, n_head, k, n_update = where
+    return text[:k + n_update] + POST_LOOP + text[k + n_update:]
+
+
 def reorder_mode_loop(text, where, nn_mode):
     j, n_head, k, n_update = where
     head = '''      // libpnn_cuda: modes in the order 0..%d, %d..34, %d (the posted neural-network request is collected last); the costs
@@ -150,7 +180,7 @@ def reorder_mode_loop(text, where, nn_mode):
                                    CandCostList);
       }
 '''
-    return text[:j] + head + text[j + n_head:k] + tail + text[k + n_update:]
+    return text[:j] + head + text[j + n_head:k] + tail + POST_LOOP + text[k + n_update:]
 
 
 def nn_mode_of_loop(prediction_cpp_text):
@@ -170,8 +200,7 @@ def main():
         text = open(os.path.join(sys.argv[3], 'TEncSearch.cpp'), encoding='latin-1').read()
         text, where = patch_search_cpp(text)
         nn_mode = nn_mode_of_loop(open(os.path.join(src, 'TComPrediction.cpp'), encoding='latin-1').read())
-        if nn_mode is not None:
-            text = reorder_mode_loop(text, where, nn_mode)
+        text = reorder_mode_loop(text, where, nn_mode) if nn_mode is not None else add_post_loop(text, where)
         open(os.path.join(sys.argv[4], 'TEncSearch.cpp'), 'w', encoding='latin-1').write(text)
         print('patched TEncSearch.cpp (prefetch%s) -> %s' % ('' if nn_mode is None else ', neural-network mode %d evaluated last' % nn_mode, sys.argv[4]))
     os.makedirs(out, exist_ok=True)

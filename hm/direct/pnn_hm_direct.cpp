@@ -142,6 +142,12 @@ int prefetch(pnn_handle* handle, int width) {
     return 0;
 }
 
+int prefetch_first_quadrant(pnn_handle* handle, int width) {
+    static const bool enabled(getenv("PNN_HM_PREFETCH_QUADRANT") ? atoi(getenv("PNN_HM_PREFETCH_QUADRANT")) != 0 : true);
+    if (!enabled) return 0;
+    return prefetch(handle, width);
+}
+
 int predict(pnn_handle* handle, int width, int* piPred, int stride) {
     const std::chrono::steady_clock::time_point t0(std::chrono::steady_clock::now());
     const int code(pnn_predict_hm(handle, width, piPred, stride));

@@ -36,6 +36,11 @@ int set_context(pnn_handle* handle, int width, const int* piRoiOrigin, int iPicS
 // other modes.  PNN_HM_PREFETCH=0 turns it off (A/B measurements with one executable).
 int prefetch(pnn_handle* handle, int width);
 
+// After the mode loop of the fast pass: the same for the top-left quadrant of the PU (initIntraPatternChType has just been run
+// on it), whose context is final already; the answer waits in the memo until the codec reaches that PU.
+// PNN_HM_PREFETCH_QUADRANT=0 turns it off.
+int prefetch_first_quadrant(pnn_handle* handle, int width);
+
 // NN branch of predIntraAng: prediction of the staged context into HM's Pel buffer
 int predict(pnn_handle* handle, int width, int* piPred, int stride);
 

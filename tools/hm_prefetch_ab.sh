@@ -7,9 +7,9 @@ VARIANT=${VARIANT:-substitution}
 SIZE=${SIZE:---width 1920 --height 1080}
 timeout -s KILL 200 python hm/run_hm.py --variant $VARIANT --backend direct --width 416 --height 240 --qps 32 > /dev/null 2>&1
 for P in ${ORDER:-0 1 0 1}; do
-  echo "== PNN_HM_PREFETCH=$P"
+  echo "== ${VAR:-PNN_HM_PREFETCH}=$P"
   rm -rf /tmp/hm_ab_$P; 
-  PNN_HM_PREFETCH=$P timeout -s KILL 600 python hm/run_hm.py --variant $VARIANT --backend direct --qps $QPS $SIZE --keep /tmp/hm_ab_$P 2>&1 | python -c "
+  env ${VAR:-PNN_HM_PREFETCH}=$P timeout -s KILL 600 python hm/run_hm.py --variant $VARIANT --backend direct --qps $QPS $SIZE --keep /tmp/hm_ab_$P 2>&1 | python -c "
 import json, sys
 for line in sys.stdin:
     line = line.strip()
