@@ -13,6 +13,8 @@ timeout -s KILL 300 python bench.py --config conv64 --steps 3 --warmup 3 > gpuru
   echo "== tools/hm_latency.py --no-fused"; timeout -s KILL 100 python tools/hm_latency.py --no-fused 2>&1 | tail -6
   echo "== tools/ref_backend_latency.py"; timeout -s KILL 200 python tools/ref_backend_latency.py 2>&1 | tail -8 ) > gpurun_out/${R}_inloop_latency.txt 2>&1
 timeout -s KILL 1500 python hm/config4.py --out gpurun_out/${R}_config3_hm_substitution_1080p.json 2>&1 | tail -30
+timeout -s KILL 400 python bench.py --config hm > gpurun_out/${R}_bench_hm.json 2>/dev/null
+( VARIANT=switch ORDER="0 1" VAR=PNN_HM_PREFETCH_QUADRANT bash tools/hm_prefetch_ab.sh ) > gpurun_out/${R}_hm_prefetch_quadrant_ab_switch_1080p.txt 2>&1
 python - <<PY
 import json
 d = json.load(open('gpurun_out/${R}_bench_n1.json'))

@@ -24,4 +24,8 @@ for width, is_fc in ((4, True), (8, False), (16, False), (32, False)):
             eng.set_hm_fused(fused)
             eng.set_context(width, plane, width + 3, width + 5, flags, int(flags.sum()))
             eng.predict_hm(width)
+        eng.set_hm_fused(True)
+        eng.set_context(width, plane, width + 3, width + 5, flags, int(flags.sum()))
+        eng.predict_hm_begin(width)                      # posted ahead, collected by the call that follows
+        eng.predict_hm(width)
 print('sanitize workload done')
