@@ -9,6 +9,8 @@ per-block statistics to rank 0, which reduces them to the reference's dictionary
 The blocks of different images are independent, so the shards need no data-path collective; the gather
 moves <= tens of MB and is latency-bound.
 """
+import os
+
 import numpy
 
 
@@ -49,6 +51,88 @@ def evaluate_blocks(engine, images_uint8, width_target, is_fully_connected, rows
         'frequency_win_pnn': float(numpy.count_nonzero(psnrs_pnn - psnrs_hevc > 0.)) / n,
         'predictions_pnn_uint8': pnn['predictions_uint8'],
     }
+
+
+def masks_training_and_validation(width_target):
+    """The five training maskings and the four test maskings of the reference's driver
+    (comparing_pnn_ipfcns_hevc_best_mode.py:501-513); `()` is the model trained with random masks."""
+    w = width_target
+    return ((0, 0), (0, w), (w, 0), (w, w), ()), ((0, 0), (0, w), (w, 0), (w, w))
+
+
+def find_model(path_to_directory_load_save):
+    """The model with the longest training in a `masks_tr_*` directory, or None
+    (comparing_pnn_ipfcns_hevc_best_mode.py:418-433: `model_<iterations>.ckpt`, chosen through its `.ckpt.meta` file).
+
+    Accepted forms, in this order: an exported flat binary `model_<iterations>.pnnw`, the TensorFlow V2 checkpoint itself
+    (`model_<iterations>.ckpt.index` + `.data-00000-of-00001`, read without TensorFlow by `weights.read_tf_v2_bundle`).
+    Returns (kind, path-or-prefix, iterations)."""
+    if not os.path.isdir(path_to_directory_load_save):
+        return None
+    found = {}
+    for name in os.listdir(path_to_directory_load_save):
+        for kind, extension in (('pnnw', '.pnnw'), ('checkpoint', '.ckpt.index'), ('checkpoint', '.ckpt.meta')):
+            if name.startswith('model_') and name.endswith(extension):
+                try:
+                    iterations = int(name[len('model_'):-len(extension)])
+                except ValueError:
+                    continue      # (tools/tools.py:175-183: a name whose middle is not an integer is ignored)
+                if kind == 'checkpoint' and not os.path.exists(os.path.join(path_to_directory_load_save, 'model_%d.ckpt.index' % iterations)):
+                    continue
+                found.setdefault(iterations, set()).add(kind)
+    if not found:
+        return None
+    iterations = max(found)
+    if 'pnnw' in found[iterations]:
+        return 'pnnw', os.path.join(path_to_directory_load_save, 'model_%d.pnnw' % iterations), iterations
+    return 'checkpoint', os.path.join(path_to_directory_load_save, 'model_%d.ckpt' % iterations), iterations
+
+
+def predict_masks(engine, images_uint8, width_target, is_fully_connected, rows, cols, path_to_directory_coeffs_load_save,
+                  image_index=None, tuples_width_height_masks_tr=None, tuples_width_height_masks_val=None,
+                  path_to_directory_coeffs_vis=None):
+    """The driver loop of the reference's offline comparison (`predict_masks`,
+    comparing_pnn_ipfcns_hevc_best_mode.py:324-452): every PNN model trained with one masking (sub-directories
+    `masks_tr_<w>_<h>` and `masks_tr_random` of `path_to_directory_coeffs_load_save`; a missing directory or one without a model
+    is skipped, the model with the longest training is taken) is evaluated under every test masking, against the best HEVC
+    mode on the same blocks.  `rows` / `cols` are the top-left pixels of the TARGET blocks (reference: `row_1sts + W`).
+    Returns {tag_masks_tr: {tag_masks_val: dictionary of `evaluate_blocks`}}; with `path_to_directory_coeffs_vis` each
+    dictionary's scalars are also written as `<vis>/<tag_tr>/<tag_val>/dictionary_performance.pkl` (protocol 2, the
+    reference's file name; IPFCN-S, a Caffe model, is out of scope)."""
+    import pickle
+    import tempfile
+
+    from . import weights as weights_module
+    default_tr, default_val = masks_training_and_validation(width_target)
+    tuples_tr = default_tr if tuples_width_height_masks_tr is None else tuples_width_height_masks_tr
+    tuples_val = default_val if tuples_width_height_masks_val is None else tuples_width_height_masks_val
+    results = {}
+    for masks_tr in tuples_tr:
+        tag_masks_tr = 'masks_tr_{0}_{1}'.format(masks_tr[0], masks_tr[1]) if masks_tr else 'masks_tr_random'
+        model = find_model(os.path.join(path_to_directory_coeffs_load_save, tag_masks_tr))
+        if model is None:
+            continue
+        kind, path, _ = model
+        if kind == 'checkpoint':
+            with tempfile.TemporaryDirectory(prefix='pnn_export_') as tmp:
+                flat = os.path.join(tmp, 'model.pnnw')
+                weights_module.export_checkpoint(path, width_target, is_fully_connected, flat)
+                engine.load_net(flat)
+        else:
+            engine.load_net(path)
+        results[tag_masks_tr] = {}
+        for masks_val in tuples_val:
+            tag_masks_val = 'masks_val_{0}_{1}'.format(masks_val[0], masks_val[1])
+            out = evaluate_blocks(engine, images_uint8, width_target, is_fully_connected, rows, cols, image_index,
+                                  masks=tuple(masks_val))
+            results[tag_masks_tr][tag_masks_val] = out
+            if path_to_directory_coeffs_vis is not None:
+                path_to_directory_vis = os.path.join(path_to_directory_coeffs_vis, tag_masks_tr, tag_masks_val)
+                os.makedirs(path_to_directory_vis, exist_ok=True)
+                scalars = {key: out[key] for key in ('mean_psnr_pnn', 'mean_psnr_hevc_best_mode', 'frequency_win_pnn')}
+                with open(os.path.join(path_to_directory_vis, 'dictionary_performance.pkl'), 'wb') as file:
+                    pickle.dump(scalars, file, protocol=2)
+    return results
 
 
 def gather_statistics(psnrs_local, wins_local, rank, world_size, group=None, counts=None):

@@ -348,3 +348,44 @@ def test_device_pointer_calls_contain_invalid_blocks(engine, weights_dir):
     ref = engine.predict_image_blocks(8, True, images, rows[valid], cols[valid], idx[valid])
     numpy.testing.assert_array_equal(d_u8.cpu().numpy()[valid].reshape(-1, 8, 8), ref['predictions_uint8'])
     numpy.testing.assert_array_equal(psnr[valid], ref['psnrs'])
+
+
+@pytest.mark.gpu
+def test_driver_loop_over_training_and_test_maskings(engine, weights_dir, tmp_path):
+    """offline.predict_masks: the reference's loop over PNN models (one per training masking; missing ones are skipped, the
+    longest training is taken) and test maskings, PNN against the best HEVC mode; one cell checked against the oracle."""
+    import pickle
+    import shutil
+    from context_adaptive_neural_network_based_prediction_b200 import offline
+    from oracle import context, epilogue, nets
+    width = 8
+    images = numpy.stack([helpers.synthetic_image(96, 128, s) for s in range(2)])
+    idx, rows, cols = offline.blocks_of_images(2, 96, 128, width)
+    root = tmp_path / 'models'
+    kept = {}
+    for tag, seed, iterations in (('masks_tr_0_0', 11, (10, 500)), ('masks_tr_random', 12, (40,))):
+        (root / tag).mkdir(parents=True)
+        for it in iterations:
+            path, wts = helpers.make_net_file(weights_dir, width, True, seed=seed + it, gain=helpers.GAIN[(width, True)])
+            shutil.copyfile(path, str(root / tag / ('model_%d.pnnw' % it)))
+            kept[tag] = wts                                                        # the last one = the longest training
+    (root / 'masks_tr_8_8').mkdir()                                                # a directory without a model: skipped
+    vis = tmp_path / 'vis'
+    out = offline.predict_masks(engine, images, width, True, rows, cols, str(root), image_index=idx,
+                                path_to_directory_coeffs_vis=str(vis))
+    assert sorted(out) == ['masks_tr_0_0', 'masks_tr_random']
+    assert sorted(out['masks_tr_random']) == ['masks_val_0_0', 'masks_val_0_8', 'masks_val_8_0', 'masks_val_8_8']
+    cell = out['masks_tr_0_0']['masks_val_8_0']
+    above, left, flat, targets = context.gather_image_blocks(images, idx, rows, cols, width, MEAN, 8, 0)
+    ref = nets.forward(kept['masks_tr_0_0'], width, True, (flat,))[..., 0]
+    ref_u8 = epilogue.epilogue_numpy(ref, MEAN)
+    assert (cell['predictions_pnn_uint8'] == ref_u8).mean() >= 0.999
+    psnr_ref = numpy.array([epilogue.psnr(ref_u8[i], targets[i]) for i in range(len(rows))])
+    close = numpy.isclose(cell['psnrs_pnn'], psnr_ref, rtol=0., atol=1e-9)
+    assert close.mean() >= 0.99                                                    # (blocks with a differently rounded pixel differ)
+    assert cell['frequency_win_pnn'] == numpy.count_nonzero(cell['psnrs_pnn'] - cell['psnrs_hevc_best_mode'] > 0.) / len(rows)
+    # the masking changes the prediction, and the two models differ
+    assert not numpy.array_equal(cell['predictions_pnn_uint8'], out['masks_tr_0_0']['masks_val_0_0']['predictions_pnn_uint8'])
+    assert not numpy.array_equal(cell['predictions_pnn_uint8'], out['masks_tr_random']['masks_val_8_0']['predictions_pnn_uint8'])
+    saved = pickle.load(open(str(vis / 'masks_tr_0_0' / 'masks_val_8_0' / 'dictionary_performance.pkl'), 'rb'))
+    assert saved['mean_psnr_pnn'] == cell['mean_psnr_pnn'] and saved['frequency_win_pnn'] == cell['frequency_win_pnn']

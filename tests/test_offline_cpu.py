@@ -113,3 +113,20 @@ def test_reduce_statistics_device_matches_numpy():
     assert abs(a['mean_psnr_pnn'] - b['mean_psnr_pnn']) < 1e-12
     assert a['frequency_win_pnn'] == b['frequency_win_pnn']
     numpy.testing.assert_array_equal(a['psnrs_pnn'], b['psnrs_pnn'])
+
+
+def test_driver_loop_finds_the_model_with_the_longest_training(tmp_path):
+    """`predict_masks` (comparing_pnn_ipfcns_hevc_best_mode.py:386-433): directory tags, skipped directories, latest model."""
+    tr, val = offline.masks_training_and_validation(8)
+    assert tr == ((0, 0), (0, 8), (8, 0), (8, 8), ()) and val == ((0, 0), (0, 8), (8, 0), (8, 8))
+    assert offline.find_model(str(tmp_path / 'masks_tr_0_0')) is None              # no such directory
+    d = tmp_path / 'masks_tr_random'
+    d.mkdir()
+    assert offline.find_model(str(d)) is None                                      # no model in it
+    for name in ('model_1000.pnnw', 'model_30000.pnnw', 'model_x.pnnw', 'model_200000.ckpt.meta', 'notes.txt'):
+        (d / name).write_bytes(b'')
+    assert offline.find_model(str(d)) == ('pnnw', str(d / 'model_30000.pnnw'), 30000)   # a .meta without its .index is no model
+    (d / 'model_200000.ckpt.index').write_bytes(b'')
+    assert offline.find_model(str(d)) == ('checkpoint', str(d / 'model_200000.ckpt'), 200000)
+    (d / 'model_200000.pnnw').write_bytes(b'')
+    assert offline.find_model(str(d))[0] == 'pnnw'                                 # the exported form of the same model wins
