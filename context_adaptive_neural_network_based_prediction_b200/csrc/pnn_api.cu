@@ -88,6 +88,11 @@ struct DevBuf {
         CUDA_TRY(cudaMalloc(&p, n));
         bytes = n;
     }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
     ~DevBuf() {
         if (p) cudaFree(p);
     }
@@ -144,6 +149,7 @@ struct Net {
     int64_t cap = 0;
     std::vector<std::unique_ptr<DevBuf>> ws0, ws1;
     DevBuf out_raw, out_u8, out_i32, out_psnr;
+    int64_t cap_limit = (int64_t)1 << 40;     // ensure_workspace_fit: the largest capacity that fitted when memory was short
     // in-loop (batch-1) path: captured launch sequence; FC nets of width <= 8: per-CTA weight images (kernel_fc_inloop.cu)
     // and the activation vectors of the layer-per-launch fall-back
     cudaGraphExec_t hm_exec = nullptr;
@@ -769,6 +775,7 @@ int64_t choose_capacity(pnn_handle* h, const Net& net, int64_t n) {
     int64_t cap = std::max<int64_t>(1, (int64_t)(budget / (size_t)per));
     // keep rows (cap * positions) comfortably inside int32
     cap = std::min<int64_t>(cap, (int64_t)1 << 19);
+    cap = std::min<int64_t>(cap, net.cap_limit);
     return std::min(cap, std::max<int64_t>(n, 1));
 }
 
@@ -804,6 +811,53 @@ Act act_of(Net& net, int buf) {
 
 // Makes the tcgen05 weight tiles of `net` on `stream`, ahead of the first launches that read them (same stream: ordered).
 // The caller has asked the persistent kernel to leave.
+// The activation workspace of a net (everything ensure_workspace made): given back when device memory runs short.
+void release_workspace(Net& net) {
+    net.drop_hm_graph();
+    for (auto& b : net.ws0) b->release();
+    for (auto& b : net.ws1) b->release();
+    net.out_raw.release();
+    net.out_u8.release();
+    net.out_i32.release();
+    net.out_psnr.release();
+    net.cap = 0;
+}
+
+// ensure_workspace under memory pressure (another engine or framework on the same GPU; the budget is per net and five nets
+// may be loaded): when an allocation fails, first the workspaces of the OTHER nets of the handle are given back (they grow
+// again on their next call), then the capacity is halved until it fits -- a batch is cut into more chunks, and a block's
+// prediction does not depend on the chunk it is computed in.  Returns the capacity that was allocated.
+int64_t ensure_workspace_fit(pnn_handle* h, Net& net, int64_t cap) {
+    bool others_released = false;
+    for (;;) {
+        try {
+            ensure_workspace(net, cap);
+            return cap;
+        } catch (const std::exception&) {
+            cudaGetLastError();                                     // (an allocation failure is not sticky)
+            if (!others_released) {
+                others_released = true;
+                bool any = false;
+                {
+                    std::unique_lock<std::mutex> lock(h->mu, std::defer_lock);
+                    if (h->bg_active.load()) lock.lock();
+                    for (auto& kv : h->nets) {
+                        if (kv.second.get() != &net && kv.second->cap > 0) {
+                            release_workspace(*kv.second);
+                            any = true;
+                        }
+                    }
+                }
+                if (any) continue;
+            }
+            if (cap <= 16) throw;
+            release_workspace(net);                                 // (some of its buffers already have the larger size)
+            cap = (cap + 1) / 2;
+            net.cap_limit = cap;                                    // nested calls of this request must not ask for more again
+        }
+    }
+}
+
 void ensure_tiles(pnn_handle* h, Net& net, cudaStream_t stream) {
     if (net.tile_jobs.empty() || h->precision != PNN_PRECISION_BF16X3) return;
     for (const Net::TileJob& job : net.tile_jobs) h->launches += launch_make_tc_tiles(job.w, job.K, job.N, job.tiles, stream);
@@ -941,8 +995,7 @@ void image_blocks_device(pnn_handle* h, Net& net, const uint8_t* d_images, int n
     const int W = net.W;
     const int64_t px = (int64_t)W * W;
     const bool split = h->precision == PNN_PRECISION_BF16X3;
-    const int64_t cap = choose_capacity(h, net, n);
-    ensure_workspace(net, cap);
+    const int64_t cap = ensure_workspace_fit(h, net, choose_capacity(h, net, n));
     ensure_tiles(h, net, stream);
     for (int64_t s0 = 0; s0 < n; s0 += cap) {
         const int64_t m = std::min(cap, n - s0);
@@ -996,8 +1049,7 @@ void batch_device(pnn_handle* h, Net& net, const float* d_a, const float* d_l, i
     const int W = net.W;
     const int64_t px = (int64_t)W * W;
     const bool split = h->precision == PNN_PRECISION_BF16X3;
-    const int64_t cap = choose_capacity(h, net, n);
-    ensure_workspace(net, cap);
+    const int64_t cap = ensure_workspace_fit(h, net, choose_capacity(h, net, n));
     ensure_tiles(h, net, stream);
     for (int64_t s0 = 0; s0 < n; s0 += cap) {
         const int64_t m = std::min(cap, n - s0);
@@ -2203,6 +2255,7 @@ int pnn_set_workspace_budget(pnn_handle* h, int64_t bytes_per_net) {
         return -1;
     }
     h->workspace_budget = (size_t)bytes_per_net;
+    for (auto& kv : h->nets) kv.second->cap_limit = (int64_t)1 << 40;     // a limit found under memory pressure is forgotten
     return 0;
 }
 
@@ -2251,7 +2304,7 @@ int pnn_predict_batch(pnn_handle* h, int width, int is_fc, const float* a, const
         const int64_t chunk = std::min<int64_t>(n, std::max<int64_t>(1, ((int64_t)1 << 28) / (5 * px * 4)));
         h->d_in0.reserve((size_t)chunk * na * 4);
         if (!is_fc) h->d_in1.reserve((size_t)chunk * 2 * px * 4);
-        ensure_workspace(net, choose_capacity(h, net, chunk));
+        ensure_workspace_fit(h, net, choose_capacity(h, net, chunk));
         DevBuf& d_out = net.out_raw;
         d_out.reserve((size_t)chunk * px * 4);
         for (int64_t s0 = 0; s0 < n; s0 += chunk) {
@@ -2332,8 +2385,7 @@ static int image_blocks_host(pnn_handle* h, int width, int is_fc, const uint8_t*
         CUDA_TRY(cudaEventRecord(in.uploaded, h->stream_in));
         CUDA_TRY(cudaStreamWaitEvent(s, in.uploaded, 0));
         // outputs are produced chunk by chunk into the net's own output buffers
-        const int64_t cap = choose_capacity(h, net, n);
-        ensure_workspace(net, cap);
+        const int64_t cap = ensure_workspace_fit(h, net, choose_capacity(h, net, n));
         if (!net.computed) {
             CUDA_TRY(cudaEventCreateWithFlags(&net.computed, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&net.read_back, cudaEventDisableTiming));

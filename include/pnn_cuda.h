@@ -241,6 +241,9 @@ int pnn_hm_cache_stats(pnn_handle* h, int64_t* hits, int64_t* misses);
 /*
  * Bytes of activation workspace one net may use (default 20 GB, or PNN_WORKSPACE_GB at pnn_create): batched calls are
  * cut into chunks that fit.  Results do not depend on it (a block's prediction is independent of its batch).
+ * The budget is an upper bound, not a reservation: a workspace grows to what the largest call so far needed, and when the
+ * device is short of memory (another engine or framework on the same GPU) the library first gives back the workspaces of
+ * the handle's other nets, then halves the chunk until it fits.
  */
 int pnn_set_workspace_budget(pnn_handle* h, int64_t bytes_per_net);
 

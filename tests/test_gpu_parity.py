@@ -389,3 +389,38 @@ def test_driver_loop_over_training_and_test_maskings(engine, weights_dir, tmp_pa
     assert not numpy.array_equal(cell['predictions_pnn_uint8'], out['masks_tr_random']['masks_val_8_0']['predictions_pnn_uint8'])
     saved = pickle.load(open(str(vis / 'masks_tr_0_0' / 'masks_val_8_0' / 'dictionary_performance.pkl'), 'rb'))
     assert saved['mean_psnr_pnn'] == cell['mean_psnr_pnn'] and saved['frequency_win_pnn'] == cell['frequency_win_pnn']
+
+
+@pytest.mark.gpu
+def test_workspace_shrinks_when_device_memory_is_short(engine, weights_dir):
+    """Another tenant holds almost all of the GPU's memory: the library gives back the workspaces of its other nets, halves its
+    chunk until the allocation fits, and returns the SAME bits as with the whole device to itself."""
+    import torch
+    width = 32
+    path, _ = helpers.make_net_file(weights_dir, width, False, seed=77, gain=helpers.GAIN[(width, False)])
+    engine.load_net(path)
+    path8, _ = helpers.make_net_file(weights_dir, 8, True, seed=78, gain=helpers.GAIN[(8, True)])
+    engine.load_net(path8)
+    images = numpy.stack([helpers.synthetic_image(320, 480, s) for s in range(8)])
+    idx, rows, cols = __import__('context_adaptive_neural_network_based_prediction_b200.offline', fromlist=['offline']).blocks_of_images(8, 320, 480, width)
+    assert len(rows) == 8 * 126
+    idx8, rows8, cols8 = __import__('context_adaptive_neural_network_based_prediction_b200.offline', fromlist=['offline']).blocks_of_images(8, 320, 480, 8)
+    engine.predict_image_blocks(8, True, images, rows8, cols8, idx8)                  # another net of the handle owns a workspace
+    engine.set_workspace_budget(1 << 40)                                              # forget any limit, start from nothing
+    free, total = torch.cuda.mem_get_info()
+    hog = torch.empty(max(free - (512 << 20), 1 << 20), dtype=torch.uint8, device='cuda')  # leave 0.5 GB: 1008 CONV-32 samples need > 1 GB
+    launches = engine.launch_count
+    try:
+        tight = engine.predict_image_blocks(width, False, images, rows, cols, idx)
+    finally:
+        del hog
+        torch.cuda.empty_cache()
+    launches_tight = engine.launch_count - launches
+    engine.set_workspace_budget(20 << 30)
+    roomy = engine.predict_image_blocks(width, False, images, rows, cols, idx)
+    assert launches_tight > engine.launch_count - launches - launches_tight          # more chunks when memory was short
+    numpy.testing.assert_array_equal(tight['predictions_uint8'], roomy['predictions_uint8'])
+    numpy.testing.assert_array_equal(tight['predictions_float32'], roomy['predictions_float32'])
+    numpy.testing.assert_array_equal(tight['psnrs'], roomy['psnrs'])
+    again = engine.predict_image_blocks(8, True, images, rows8, cols8, idx8)         # the net whose workspace was given back still works
+    assert again['predictions_uint8'].shape == (len(rows8), 8, 8)
