@@ -1261,26 +1261,43 @@ static int create_impl(const char* paths_file, float mean_training, int qp_selec
             // (TComPrediction.cpp(substitution):156)
             std::ifstream f(paths_file);
             if (!f) throw std::runtime_error(std::string("The file at \"") + paths_file + "\" cannot be opened.");
-            std::map<int, std::string> single, pair;
+            // maps keyed by (first key, third key) like the reference's; the lookups below use (width, 0)
+            std::map<std::pair<unsigned, unsigned>, std::string> single, pair;
             std::string line;
             while (std::getline(f, line)) {
-                if (line.find_first_not_of(" \t\f\v\n\r") == std::string::npos) continue;
+                if (line.find_first_not_of(" \t\f\v\n\r") == std::string::npos) continue;   // tools.cpp:3-6, 74-78
+                // split_string with the regular expression "[,]+" (tools.cpp:127-152): a run of delimiters separates two
+                // substrings; a line that begins with one has an empty first substring
                 std::vector<std::string> parts;
-                std::stringstream ss(line);
-                std::string item;
-                while (std::getline(ss, item, ',')) parts.push_back(item);
+                size_t pos = 0;
+                while (pos <= line.size()) {
+                    const size_t next = line.find(',', pos);
+                    if (next == std::string::npos) {
+                        parts.push_back(line.substr(pos));
+                        break;
+                    }
+                    parts.push_back(line.substr(pos, next - pos));
+                    pos = line.find_first_not_of(',', next);
+                    if (pos == std::string::npos) break;                      // trailing delimiters add nothing
+                }
                 if (parts.size() < 4) throw std::runtime_error("malformed line in the paths file: \"" + line + "\"");
-                const int width = std::stoi(parts[0]);
-                const bool is_pair = std::stoi(parts[1]) != 0;
+                unsigned long width = 0, is_pair = 0, third = 0;
+                try {                                                         // std::stoul, as tools.cpp:89-93
+                    width = std::stoul(parts[0]);
+                    is_pair = std::stoul(parts[1]);
+                    third = std::stoul(parts[2]);
+                } catch (const std::exception&) {
+                    throw std::runtime_error("malformed line in the paths file: \"" + line + "\"");
+                }
                 std::string p = parts[3];
                 p.erase(0, p.find_first_not_of(" \t\f\v\n\r"));
                 p.erase(p.find_last_not_of(" \t\f\v\n\r") + 1);
-                (is_pair ? pair : single)[width] = p;
+                (is_pair ? pair : single)[std::make_pair((unsigned)width, (unsigned)third)] = p;
             }
             const bool use_pair = !pair.empty() && qp_selection >= 32;
-            const std::map<int, std::string>& chosen = use_pair ? pair : single;
-            for (int width : {4, 8, 16, 32, 64}) {
-                auto it = chosen.find(width);
+            const std::map<std::pair<unsigned, unsigned>, std::string>& chosen = use_pair ? pair : single;
+            for (unsigned width : {4u, 8u, 16u, 32u, 64u}) {
+                auto it = chosen.find(std::make_pair(width, 0u));              // TComPrediction.cpp(substitution):158-170
                 if (it == chosen.end()) throw std::runtime_error("the paths file has no entry for width " + std::to_string(width));
                 register_net_impl(h.get(), it->second);
             }

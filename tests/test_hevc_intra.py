@@ -43,6 +43,29 @@ def test_oracle_matches_compiled_reference():
     assert lib.ref_hevc_intraprediction(9, 9, 4, pattern.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), 35) == -1
 
 
+def test_oracle_matches_the_reference_python_path(golden_dir):
+    """tests/golden/hevc_python_ref.npz: the reference's own Python functions -- `extract_intra_patterns`,
+    `predict_series_via_hevc_best_mode` (hevc/intraprediction/intraprediction.py:10-292), imported unmodified over the
+    reference's C++ compiled unmodified (tests/golden/make_hevc_python_golden.py) -- on 16 (width, masks) cases of 12
+    blocks, one of them in a flat area where modes tie: pattern, best-mode index, PSNR and prediction of the oracle agree."""
+    data = numpy.load(os.path.join(golden_dir, 'hevc_python_ref.npz'))
+    image = data['image']
+    for i in range(int(data['n_cases'][0])):
+        width = int(data['c%d_width' % i][0])
+        mask_w, mask_h = (int(v) for v in data['c%d_masks' % i])
+        row_refs, col_refs = data['c%d_row_refs' % i], data['c%d_col_refs' % i]
+        patterns = data['c%d_patterns' % i]
+        for j in range(len(row_refs)):
+            first_row, first_col = hevc_intra.extract_intra_pattern(image, width, int(row_refs[j]), int(col_refs[j]), mask_w, mask_h)
+            numpy.testing.assert_array_equal(first_row, patterns[j, 0, :, 0])
+            numpy.testing.assert_array_equal(first_col, patterns[j, :, 0, 0])
+        idx, psnrs, preds = hevc_intra.best_modes_of_blocks(image[None], numpy.zeros(len(row_refs), dtype=int), row_refs + 1, col_refs + 1,
+                                                            width, mask_w, mask_h)
+        numpy.testing.assert_array_equal(idx, data['c%d_indices' % i], err_msg='case %d' % i)
+        numpy.testing.assert_allclose(psnrs, data['c%d_psnrs' % i], rtol=0., atol=1e-9)
+        numpy.testing.assert_array_equal(preds, data['c%d_preds' % i][..., 0])
+
+
 def test_best_mode_rule():
     """reference intraprediction.py:262-292: the first mode with the strictly highest PSNR wins; flat content -> planar (0)."""
     flat_row, flat_col = numpy.full(9, 77, dtype=numpy.int64), numpy.full(9, 77, dtype=numpy.int64)

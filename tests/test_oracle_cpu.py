@@ -385,3 +385,27 @@ def test_cpu_baseline_backend_matches_the_oracle(tmp_path):
         assert lib.pnn_predict_hm_context(h, 32, above.ctypes.data, left.ctypes.data, out.ctypes.data) == -1   # no such net
     finally:
         lib.pnn_destroy(h)
+
+
+def test_epilogue_and_metrics_against_the_reference_functions(golden_dir):
+    """tests/golden/tools_ref.npz holds the outputs of the reference's own `cast_float_to_uint8`, `compute_psnr`
+    (tools/tools.py:17-49, 364-401) and `compute_performance_neural_network_vs_hevc_best_mode`
+    (comparing_pnn_ipfcns_hevc_best_mode.py:39-88), imported unmodified by tests/golden/make_tools_golden.py:
+    the oracle's epilogue, PSNR and win frequency reproduce them exactly (ties at .5, clipping, identical blocks, PSNR ties)."""
+    g = numpy.load(os.path.join(golden_dir, 'tools_ref.npz'))
+    floats = g['floats']
+    numpy.testing.assert_array_equal(epilogue.epilogue_numpy(floats.astype(numpy.float32), 0.), g['cast32'])
+    numpy.testing.assert_array_equal(epilogue.epilogue_numpy(floats.astype(numpy.float64), 0.), g['cast64'])
+    lib = ctypes.CDLL(os.path.join(ROOT, 'oracle/_build/libpnn_oracle.so'))
+    f32 = numpy.ascontiguousarray(floats, dtype=numpy.float32)
+    out_u = numpy.zeros(f32.size, dtype=numpy.uint8)
+    lib.oracle_epilogue_numpy(f32.ctypes.data_as(ctypes.c_void_p), f32.size, ctypes.c_float(0.), out_u.ctypes.data_as(ctypes.c_void_p))
+    numpy.testing.assert_array_equal(out_u, g['cast32'])
+    psnrs = numpy.array([epilogue.psnr(a, b) for a, b in zip(g['pairs_a'], g['pairs_b'])])
+    numpy.testing.assert_allclose(psnrs, g['psnrs'], rtol=0., atol=1e-12)
+    psnrs_nn, frequency = epilogue.performance_vs_baseline(g['targets'][..., 0], g['preds'][..., 0], g['base'])
+    numpy.testing.assert_allclose(psnrs_nn, g['psnrs_nn'], rtol=0., atol=1e-12)
+    assert frequency == float(g['frequency'][1])                     # (one PSNR tie in the data: a tie is not a win)
+    from context_adaptive_neural_network_based_prediction_b200 import offline
+    wins = (psnrs_nn - g['base'] > 0.).astype(numpy.uint8)
+    assert offline.reduce_statistics(psnrs_nn, wins)['frequency_win_pnn'] == float(g['frequency'][1])
