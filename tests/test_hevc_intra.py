@@ -102,6 +102,23 @@ def test_gpu_best_mode_bit_exact(engine, width):
 
 
 @pytest.mark.gpu
+def test_gpu_best_mode_equals_the_reference_python_path(engine, golden_dir):
+    """The CUDA kernel against tests/golden/hevc_python_ref.npz directly (the reference's Python best-mode loop over its own
+    C++, see test_oracle_matches_the_reference_python_path): indices, predictions and PSNRs, no oracle in between."""
+    data = numpy.load(os.path.join(golden_dir, 'hevc_python_ref.npz'))
+    image = numpy.ascontiguousarray(data['image'])[None]
+    for i in range(int(data['n_cases'][0])):
+        width = int(data['c%d_width' % i][0])
+        masks = tuple(int(v) for v in data['c%d_masks' % i])
+        rows = (data['c%d_row_refs' % i] + 1).astype(numpy.int32)
+        cols = (data['c%d_col_refs' % i] + 1).astype(numpy.int32)
+        out = engine.hevc_best_mode(width, image, rows, cols, numpy.zeros(len(rows), dtype=numpy.int32), masks=masks)
+        numpy.testing.assert_array_equal(out['indices_hevc_best_mode'], data['c%d_indices' % i], err_msg='case %d' % i)
+        numpy.testing.assert_array_equal(out['predictions_hevc_best_mode_uint8'], data['c%d_preds' % i][..., 0])
+        numpy.testing.assert_allclose(out['psnrs_hevc_best_mode'], data['c%d_psnrs' % i], rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
 def test_gpu_best_mode_errors(engine):
     from context_adaptive_neural_network_based_prediction_b200 import PnnError
     img = helpers.synthetic_image(64, 64, 0)
