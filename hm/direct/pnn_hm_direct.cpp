@@ -19,6 +19,7 @@ double g_seconds[5] = {0., 0., 0., 0., 0.};
 double g_first_seconds[5] = {0., 0., 0., 0., 0.};   // the first call of a width: device initialisation (first width) and the upload of the net
 long long g_posts[5] = {0, 0, 0, 0, 0};             // requests posted ahead of their use (prefetch)
 bool g_first_done[5] = {false, false, false, false, false};
+bool g_cache_enabled = true;   // without the memo an answer that is not collected by the very next call would be lost: nothing is posted ahead
 
 int width_index(int width) { return width == 4 ? 0 : width == 8 ? 1 : width == 16 ? 2 : width == 32 ? 3 : 4; }
 
@@ -100,7 +101,8 @@ pnn_handle* create(const std::string& path_to_file_paths_to_graphs_output, float
         return NULL;
     }
     const char* cache = getenv("PNN_HM_CACHE");
-    pnn_set_hm_cache(g_handle, cache ? atoi(cache) : 1);
+    g_cache_enabled = cache ? atoi(cache) != 0 : true;
+    pnn_set_hm_cache(g_handle, g_cache_enabled ? 1 : 0);
     // HM does not touch the reconstruction between initIntraPatternChType and predIntraAng: the context is copied only
     // when the neural-network mode is actually evaluated
     pnn_set_context_lazy(g_handle, 1);
@@ -128,7 +130,7 @@ int set_context(pnn_handle* handle, int width, const int* piRoiOrigin, int iPicS
 
 int prefetch(pnn_handle* handle, int width) {
     static const bool enabled(getenv("PNN_HM_PREFETCH") ? atoi(getenv("PNN_HM_PREFETCH")) != 0 : true);
-    if (!enabled) return 0;
+    if (!enabled || !g_cache_enabled) return 0;
     const std::chrono::steady_clock::time_point t0(std::chrono::steady_clock::now());
     const int code(pnn_predict_hm_begin(handle, width));
     const double dt(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
